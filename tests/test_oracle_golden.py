@@ -1,0 +1,157 @@
+"""Pin the oracle (oracle/psmf_oracle.py) against the reference's golden vectors.
+
+* published per-repeat goldens of the reference run (PM25 30 %, repeat 0;
+  ExperimentImpute/output/LondonAir_PM25_30_{PSMF,rPSMF}.json)
+* reference-generated fixtures (tests/golden/make_golden.py): X trajectory,
+  per-step eta / a / P+Q captured from the unmodified loop body
+* pypsmf class fixtures (full step with cos dynamics, robust, scaled, random walk,
+  simplified synthetic classes)
+
+fp64 tolerance: 1e-9 norm-wise per quantity (max|delta| / max|ref|).
+"""
+
+import numpy as np
+import pytest
+
+from conftest import impute_case, load_golden, relerr
+from oracle import psmf_oracle as po
+
+TOL = 1e-9
+
+
+def _run_impute(g, method):
+    c = impute_case(g)
+    r = c["r"]
+    d, n = c["Y"].shape
+    X = c["X0"].copy()
+    Einit = po.rmsem(c["C0"] @ X, c["YorigInt"], c["Mmiss"])
+    rec = []
+    robust = method == "rPSMF"
+    # replay with a per-step record
+    cfg = po.OracleConfig(robust=robust, c_update_transpose=robust, bounds_rpsmf=robust, sig=2.0)
+    st = po.OracleState(c["C0"].copy(), X[:, n - 1].copy(), np.eye(r), 2 * np.eye(r), 0.1 * np.eye(r), 10.0, 1.8)
+    Mf = c["M"].astype(float)
+    eta, a, PP = [], [], []
+    for i in range(c["Iter"]):
+        st.Q = 0.1 * np.eye(r); st.rho = 10.0; st.lam = 1.8
+        st.x = X[:, n - 1].copy()
+        for t in range(n):
+            PP.append(st.P + st.Q)
+            st, out = po.step(st, cfg, c["Y"][:, t], Mf[:, t])
+            X[:, t] = st.x
+            eta.append(out["eta"]); a.append(out["a"])
+    Ep, Ef, ib, st2, *_ = po.impute_fit(c["Y"], c["C0"], c["X0"].copy(), c["M"], c["Mmiss"], 2 * np.eye(r),
+                                        0.1 * np.eye(r), 10.0, np.eye(r), 1.8, 2.0, c["Iter"], c["YorigInt"],
+                                        Einit, robust)
+    return dict(X=X, eta=np.array(eta), a=np.array(a), PP=np.stack(PP), Ep=Ep, Ef=Ef, ib=ib, Einit=Einit)
+
+
+@pytest.mark.parametrize("method", ["rPSMF", "PSMF"])
+def test_published_golden_pm25(method):
+    g = load_golden("impute_pm25_30")
+    res = _run_impute(g, method)
+    pub = g["rep0_%s_published" % method]          # error_predict, error_full, inside_sig
+    assert abs(res["Ep"][0, -1] - pub[0]) / pub[0] < 1e-10
+    assert abs(res["Ef"][0, -1] - pub[1]) / pub[1] < 1e-10
+    assert abs(res["ib"] - pub[2]) < 1e-12
+    pre = "rep0_%s_" % method
+    assert relerr(res["X"], g[pre + "X_final"]) < TOL
+    assert relerr(res["eta"], g[pre + "eta"]) < TOL
+    assert relerr(res["a"], g[pre + "a"]) < TOL
+    assert relerr(res["PP"][g[pre + "PP_idx"]], g[pre + "PP"]) < TOL
+    assert relerr(res["Ep"], g[pre + "Epred"]) < TOL
+    assert relerr(res["Ef"], g[pre + "Efull"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["impute_pm10_head_20", "impute_sp500_head_30"])
+@pytest.mark.parametrize("method", ["rPSMF", "PSMF"])
+def test_reference_fixture(name, method):
+    g = load_golden(name)
+    res = _run_impute(g, method)
+    pre = "rep0_%s_" % method
+    assert relerr(res["X"], g[pre + "X_final"]) < TOL
+    assert relerr(res["eta"], g[pre + "eta"]) < TOL
+    assert relerr(res["a"], g[pre + "a"]) < TOL
+    assert relerr(res["PP"][g[pre + "PP_idx"]], g[pre + "PP"]) < TOL
+    assert relerr(res["Ep"], g[pre + "Epred"]) < TOL
+    assert relerr(res["Ef"], g[pre + "Efull"]) < TOL
+    assert abs(res["ib"] - float(g[pre + "inside"])) < 1e-12
+
+
+def _pypsmf_run(g, tag, robust, dyn, simplified=False):
+    Y = g[tag + "_Y"]
+    T, d = Y.shape
+    C0 = g[tag + "_C0"]
+    r = C0.shape[1]
+    theta = g[tag + "_theta0"] if (tag + "_theta0") in g else None
+    alpha = float(g[tag + "_alpha"]) if (tag + "_alpha") in g else 1.0
+    beta = float(g[tag + "_beta"]) if (tag + "_beta") in g else 1.0
+    cfg = po.OracleConfig(robust=robust, simplified=simplified, c_update_transpose=True, bounds_rpsmf=robust,
+                          alpha=alpha, beta=beta, dynamics=dyn)
+    lam0 = float(g[tag + "_lam0"]) if (tag + "_lam0") in g else 0.0
+    st = po.OracleState(C0.copy(), g[tag + "_mu0"].copy(), g[tag + "_P0"].copy(), g[tag + "_V0"].copy(),
+                        g[tag + "_Q"].copy(), float(g[tag + "_rho"]), lam0, theta)
+    st, X, Yrec, scal = po.run(st, cfg, Y, None, k0=1)
+    return st, X, Yrec, scal
+
+
+@pytest.mark.parametrize("tag,robust,dyn", [
+    ("psmf_full", False, po.DYN_COS),
+    ("rpsmf_full", True, po.DYN_COS),
+    ("rpsmf_scaled", True, po.DYN_COS),
+    ("psmf_rw", False, po.DYN_IDENTITY),
+])
+def test_pypsmf_fixture(tag, robust, dyn):
+    g = load_golden("pypsmf_cases")
+    st, X, Yrec, scal = _pypsmf_run(g, tag, robust, dyn)
+    assert relerr(Yrec, g[tag + "_ypred"]) < TOL
+    assert relerr(st.C, g[tag + "_C"]) < TOL
+    assert relerr(st.x, g[tag + "_mu"]) < TOL
+    assert relerr(st.P, g[tag + "_P"]) < TOL
+    assert relerr(st.V, g[tag + "_V"]) < TOL
+    if robust:
+        assert relerr(st.lam, g[tag + "_lam_T"]) < TOL
+        assert relerr(st.rho, g[tag + "_rho_T"]) < TOL
+        assert relerr(st.Q, g[tag + "_Q_T"]) < TOL
+
+
+@pytest.mark.parametrize("tag,robust", [("syn_psmf", False), ("syn_rpsmf", True)])
+def test_simplified_synthetic_first_sweep(tag, robust):
+    """Configs 1-2 (shortened): first sweep with theta0 (synthetic_psmf.py:78-100, synthetic_rpsmf.py:82-118)."""
+    g = load_golden("pypsmf_cases")
+    Y = g[tag + "_Y"]
+    T, d = Y.shape
+    C0 = g[tag + "_C0"]
+    r = C0.shape[1]
+    cfg = po.OracleConfig(robust=robust, simplified=True, dynamics=po.DYN_COS)
+    st = po.OracleState(C0.copy(), np.zeros(r), np.zeros((r, r)), g[tag + "_V0"].copy(), np.zeros((r, r)), 1.0,
+                        1.8 if robust else 0.0, g[tag + "_thetas"][0])
+    st, X, Yrec, scal = po.run(st, cfg, Y, None, k0=1)
+    assert relerr(st.C, g[tag + "_Cs"][0]) < TOL
+    assert relerr(st.x, g[tag + "_mus"][0]) < TOL
+    # the general (non-simplified) formulas coincide when P0 = 0 and Q = 0
+    cfg2 = po.OracleConfig(robust=robust, simplified=False, dynamics=po.DYN_COS)
+    st2 = po.OracleState(C0.copy(), np.zeros(r), np.zeros((r, r)), g[tag + "_V0"].copy(), np.zeros((r, r)), 1.0,
+                         1.8 if robust else 0.0, g[tag + "_thetas"][0])
+    st2, *_ = po.run(st2, cfg2, Y, None, k0=1)
+    assert relerr(st2.C, st.C) < 1e-12
+
+
+@pytest.mark.parametrize("tag,robust", [("syn_psmf", False), ("syn_rpsmf", True)])
+def test_theta_gradient_closed_form(tag, robust):
+    """sum_k d ell_k / d theta over the first sweep vs the reference's _gradsum (finite-difference shim: 1e-6)."""
+    g = load_golden("pypsmf_cases")
+    Y = g[tag + "_Y"]
+    T, d = Y.shape
+    C0 = g[tag + "_C0"]
+    r = C0.shape[1]
+    theta = g[tag + "_thetas"][0]
+    cfg = po.OracleConfig(robust=robust, simplified=True, dynamics=po.DYN_COS)
+    st = po.OracleState(C0.copy(), np.zeros(r), np.zeros((r, r)), g[tag + "_V0"].copy(), np.zeros((r, r)), 1.0,
+                        1.8 if robust else 0.0, theta)
+    gs = np.zeros(r)
+    for k in range(1, T + 1):
+        eta = st.rho
+        gs += po.theta_grad_cos(robust, theta, st.x, k, Y[k - 1], st.C, st.V, eta, st.lam, d)
+        st, _ = po.step(st, cfg, Y[k - 1], None, k=k)
+    assert relerr(gs, g[tag + "_grads"][0]) < 1e-6
