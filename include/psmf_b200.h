@@ -1,0 +1,142 @@
+/*
+ * psmf_b200.h -- C ABI of the B200-native PSMF / rPSMF per-timestep filter.
+ *
+ * This is the drop-in boundary for the reference's filter hot path.  The
+ * reference (alan-turing-institute/rPSMF) has no FFI of its own: its boundary
+ * is two Python surfaces, which the package rpsmf_b200/ re-creates on top of
+ * this library through ctypes:
+ *
+ *   flat model functions   ExperimentImpute/rPSMF.py:39-148  robust_PSMF(...)
+ *                          ExperimentImpute/PSMF.py:39-95    ProbabilisticSequentialMatrixFactorizer(...)
+ *   class surface          pypsmf/psmf/psmf.py:14-248,275-331   PSMFIter, PSMFRecursive
+ *                          pypsmf/psmf/rpsmf.py:11-184,187-334  rPSMFIter, rPSMFIterMissing, rPSMFRecursive
+ *
+ * Conventions
+ *   - every buffer is a CALLER-OWNED DEVICE pointer (e.g. torch tensor
+ *     data_ptr()); the library never frees it.  The library owns only its
+ *     workspace (tiled copy of C, reduction scratch, NVLink mailboxes).
+ *   - all functions return 0 on success, <0 on error (PSMF_E_*); the text of the
+ *     last error of a handle is available from psmf_last_error().  Nothing
+ *     throws or exits across the ABI.
+ *   - one host thread per handle.  Kernels are enqueued on the caller's stream
+ *     (a cudaStream_t passed as void*); psmf_run does not synchronise.
+ *   - small state (x, P, V, Q, theta, rho, lambda) is always float64.  `dtype`
+ *     selects the storage type of C, Y and Yrec (f64 or f32); all reductions
+ *     and the r x r solves are float64 in both modes.
+ */
+#ifndef PSMF_B200_H
+#define PSMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct psmf_engine* psmf_handle;
+
+#define PSMF_MAX_RANK 16
+#define PSMF_MAX_PEERS 8
+
+/* storage dtype of C / Y / Yrec */
+#define PSMF_F64 0
+#define PSMF_F32 1
+
+/* flags */
+#define PSMF_ROBUST        1   /* rPSMF: Student-t scales omega/phi, Q,R,lambda evolve (rPSMF.py:105,112-115,133-135) */
+#define PSMF_SIMPLIFIED    2   /* ExperimentSynthetic overrides: P_bar=P, eta=tr(R)/d, x_t=x_bar (synthetic_psmf.py:78-100) */
+#define PSMF_CUPDATE_VT    4   /* C += e (V x)'/N  (rPSMF.py:111, psmf.py:132); unset: C += e (V' x)'/N (PSMF.py:80) */
+#define PSMF_FIXED_LAMBDA  16  /* rpsmf.py:36-40 */
+
+/* dynamics f_theta(x, k) of the predict half (psmf.py:104-115) */
+#define PSMF_DYN_IDENTITY 0    /* RandomWalk, nonlinearities.py:42-56; Impute scripts */
+#define PSMF_DYN_COS      1    /* cos(2 pi theta k + x), synthetic_psmf.py:105-106 */
+#define PSMF_DYN_EXTERNAL 3    /* x_bar and F = df/dx supplied by the caller, one step per psmf_run */
+
+/* error codes */
+#define PSMF_OK          0
+#define PSMF_E_INVALID  -1
+#define PSMF_E_CUDA     -2
+#define PSMF_E_NOMEM    -3
+#define PSMF_E_STATE    -4
+
+/* per-step scalar record written to scal_out: (n_series, n_steps, PSMF_NSCAL) float64 */
+#define PSMF_NSCAL 8
+#define PSMF_SCAL_A      0   /* a = x_bar' V x_bar          rPSMF.py:93  */
+#define PSMF_SCAL_ETA    1   /* eta_k                        rPSMF.py:108 */
+#define PSMF_SCAL_N      2   /* N_k = a + eta                rPSMF.py:109 */
+#define PSMF_SCAL_OMEGA  3   /* omega_k                      rPSMF.py:105 */
+#define PSMF_SCAL_PHI    4   /* phi_k                        rPSMF.py:114 */
+#define PSMF_SCAL_SSE    5   /* e' S^-1 e                    rPSMF.py:105 */
+#define PSMF_SCAL_LAMBDA 6   /* lambda entering the step */
+#define PSMF_SCAL_RHO    7   /* rho (R = rho I) entering the step */
+
+typedef struct psmf_config {
+    int64_t d;          /* rows of C held by this engine (the local shard)                         */
+    int64_t d_global;   /* rows of the whole series: denominators of eta/omega/phi (== d if 1 GPU)  */
+    int32_t r;          /* latent rank, 1..PSMF_MAX_RANK                                            */
+    int32_t n_series;   /* independent series batched in this engine (>=1); no communication       */
+    int32_t dtype;      /* PSMF_F64 | PSMF_F32                                                      */
+    int32_t flags;      /* PSMF_ROBUST | ...                                                        */
+    int32_t dynamics;   /* PSMF_DYN_*                                                               */
+    int32_t device;     /* CUDA device ordinal                                                      */
+    int32_t world_size; /* GPUs sharing ONE series by rows (1 = no exchange)                       */
+    int32_t rank;
+    int32_t ctas;       /* CTAs per series, 0 = auto                                                */
+    int32_t reserved;
+    double  alpha;      /* V scale (rpsmf.py:45-51), 1.0 unless use_scaling                        */
+    double  beta;       /* P scale                                                                  */
+} psmf_config;
+
+typedef struct psmf_io {
+    const void*    Y;          /* (n_series, n_steps, ldy) time-major observations, zero-filled where missing */
+    int64_t        ldy;        /* elements between consecutive time steps (>= d)                      */
+    int64_t        y_series_stride;
+    const uint8_t* M;          /* (n_series, n_steps, ldm) 1 = observed, 0 = missing; NULL = all observed */
+    int64_t        ldm;
+    int64_t        m_series_stride;
+    double*        X_out;      /* (n_series, n_steps, r) filtered x_t, or NULL   (X[:, t], rPSMF.py:104) */
+    void*          Yrec_out;   /* (n_series, n_steps, ldrec) C x_bar (unmasked), or NULL (Yrec, rPSMF.py:89) */
+    int64_t        ldrec;
+    int64_t        rec_series_stride;
+    double*        scal_out;   /* (n_series, n_steps, PSMF_NSCAL) or NULL                             */
+    const double*  xbar_ext;   /* PSMF_DYN_EXTERNAL: (n_series, r)                                    */
+    const double*  F_ext;      /* PSMF_DYN_EXTERNAL: (n_series, r, r) row-major                       */
+} psmf_io;
+
+/* lifecycle ------------------------------------------------------------------------------------ */
+int  psmf_create(psmf_handle* out, const psmf_config* cfg);
+int  psmf_destroy(psmf_handle h);
+const char* psmf_last_error(psmf_handle h);   /* h may be NULL: error of the last failed psmf_create */
+int  psmf_version(void);
+
+/* state round trip (sweep carry-over: psmf.py:75-83, rPSMF.py:75-79).  Any pointer may be NULL = leave /
+ * skip.  C is (n_series, d, r) row-major in the engine dtype; V, P, Q are (n_series, r, r) row-major
+ * float64; x, theta (n_series, r); rho, lambda (n_series) float64.                                   */
+int  psmf_set_state(psmf_handle h, const void* C, const double* V, const double* P, const double* x,
+                    const double* Q, const double* rho, const double* lambda, const double* theta, void* stream);
+int  psmf_get_state(psmf_handle h, void* C, double* V, double* P, double* x,
+                    double* Q, double* rho, double* lambda, double* theta, void* stream);
+
+/* the hot path: n_steps filter steps starting at absolute time index k0 (the `t` argument handed to the
+ * nonlinearity for the first step; pypsmf counts from 1).                                           */
+int  psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k0, void* stream);
+
+/* synchronise the stream of the last run and report the device status word:
+ * *first_bad_step = -1 if every step produced finite N/omega/phi, else the first offending step.    */
+int  psmf_status(psmf_handle h, int64_t* first_bad_step);
+
+/* introspection used by bench.py / tests: CTAs per series, threads per CTA, dynamic smem bytes,
+ * kernels launched by the last psmf_run.                                                            */
+int  psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* smem_bytes, int32_t* launches);
+
+/* multi-GPU row sharding (world_size > 1): NVLink mailbox for the per-step statistics exchange.
+ * Each rank exports an IPC handle of its mailbox (64 bytes), gathers all ranks' handles through the
+ * host-side process group, and connects.                                                            */
+int  psmf_mailbox_export(psmf_handle h, void* ipc_handle_64B);
+int  psmf_mailbox_connect(psmf_handle h, const void* all_ipc_handles, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSMF_B200_H */

@@ -1,0 +1,318 @@
+// C ABI of the B200-native PSMF / rPSMF filter (include/psmf_b200.h).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/psmf_b200.h"
+#include "psmf_common.cuh"
+
+PSMF_DECLARE_R(1) PSMF_DECLARE_R(2) PSMF_DECLARE_R(3) PSMF_DECLARE_R(4)
+PSMF_DECLARE_R(5) PSMF_DECLARE_R(6) PSMF_DECLARE_R(7) PSMF_DECLARE_R(8)
+PSMF_DECLARE_R(9) PSMF_DECLARE_R(10) PSMF_DECLARE_R(11) PSMF_DECLARE_R(12)
+PSMF_DECLARE_R(13) PSMF_DECLARE_R(14) PSMF_DECLARE_R(15) PSMF_DECLARE_R(16)
+
+namespace psmf {
+
+static const launch_fn LAUNCH[MAXR + 1] = {
+    nullptr,           launch_filter_r1,  launch_filter_r2,  launch_filter_r3,  launch_filter_r4,  launch_filter_r5,
+    launch_filter_r6,  launch_filter_r7,  launch_filter_r8,  launch_filter_r9,  launch_filter_r10, launch_filter_r11,
+    launch_filter_r12, launch_filter_r13, launch_filter_r14, launch_filter_r15, launch_filter_r16};
+static const shape_fn SHAPE[MAXR + 1] = {
+    nullptr,          shape_filter_r1,  shape_filter_r2,  shape_filter_r3,  shape_filter_r4,  shape_filter_r5,
+    shape_filter_r6,  shape_filter_r7,  shape_filter_r8,  shape_filter_r9,  shape_filter_r10, shape_filter_r11,
+    shape_filter_r12, shape_filter_r13, shape_filter_r14, shape_filter_r15, shape_filter_r16};
+
+// (n_series, d, R) row-major  <->  tiled [tile][R][32]
+template <typename T>
+__global__ void pack_C(const T* __restrict__ src, T* __restrict__ dst, int64_t d, int R, int64_t ntiles, int64_t total) {
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)(idx % TILE);
+        const int j = (int)((idx / TILE) % R);
+        const int64_t tile = (idx / (TILE * (int64_t)R)) % ntiles;
+        const int64_t s = idx / (TILE * (int64_t)R * ntiles);
+        const int64_t row = tile * TILE + l;
+        dst[idx] = row < d ? src[(s * d + row) * R + j] : (T)0;
+    }
+}
+template <typename T>
+__global__ void unpack_C(const T* __restrict__ src, T* __restrict__ dst, int64_t d, int R, int64_t ntiles, int64_t total) {
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)(idx % TILE);
+        const int j = (int)((idx / TILE) % R);
+        const int64_t tile = (idx / (TILE * (int64_t)R)) % ntiles;
+        const int64_t s = idx / (TILE * (int64_t)R * ntiles);
+        const int64_t row = tile * TILE + l;
+        if (row < d) dst[(s * d + row) * R + j] = src[idx];
+    }
+}
+
+}  // namespace psmf
+
+using namespace psmf;
+
+struct psmf_engine {
+    psmf_config cfg;
+    int R = 0;
+    int S = 1;
+    int64_t d = 0, ntiles = 0;
+    size_t esize = 8;
+    void* C = nullptr;
+    double* state = nullptr;
+    double* partials = nullptr;
+    unsigned long long* bar = nullptr;
+    long long* status = nullptr;
+    int cps = 1, threads = 0, launches_last = 0, num_sms = 0;
+    size_t dyn_smem = 0;
+    bool cooperative = false;
+    cudaStream_t last_stream = nullptr;
+    std::string err;
+};
+
+static std::string g_create_error;
+
+static int fail(psmf_engine* h, int code, const std::string& msg) {
+    if (h)
+        h->err = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+#define CK(h, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return fail(h, PSMF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                \
+    } while (0)
+
+extern "C" int psmf_version(void) { return 100; }
+
+extern "C" const char* psmf_last_error(psmf_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static void free_engine(psmf_engine* e) {
+    if (!e) return;
+    cudaFree(e->C);
+    cudaFree(e->state);
+    cudaFree(e->partials);
+    cudaFree(e->bar);
+    cudaFree(e->status);
+    delete e;
+}
+
+extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
+    if (!out || !cfg) return fail(nullptr, PSMF_E_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->r < 1 || cfg->r > PSMF_MAX_RANK) return fail(nullptr, PSMF_E_INVALID, "rank r must be in 1..16");
+    if (cfg->d < 1) return fail(nullptr, PSMF_E_INVALID, "d must be >= 1");
+    if (cfg->n_series < 1) return fail(nullptr, PSMF_E_INVALID, "n_series must be >= 1");
+    if (cfg->dtype != PSMF_F64 && cfg->dtype != PSMF_F32) return fail(nullptr, PSMF_E_INVALID, "dtype must be PSMF_F64 or PSMF_F32");
+    if (cfg->dynamics != PSMF_DYN_IDENTITY && cfg->dynamics != PSMF_DYN_COS && cfg->dynamics != PSMF_DYN_EXTERNAL)
+        return fail(nullptr, PSMF_E_INVALID, "unknown dynamics id");
+    if (cfg->world_size < 1 || cfg->world_size > PSMF_MAX_PEERS || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+        return fail(nullptr, PSMF_E_INVALID, "bad world_size / rank");
+    if (cfg->world_size > 1 && cfg->n_series > 1)
+        return fail(nullptr, PSMF_E_INVALID, "row sharding (world_size > 1) and batching (n_series > 1) are exclusive");
+    if (cfg->world_size > 1) return fail(nullptr, PSMF_E_INVALID, "world_size > 1: mailbox exchange not built yet");
+    const int64_t dg = cfg->d_global > 0 ? cfg->d_global : cfg->d;
+    if (dg < cfg->d) return fail(nullptr, PSMF_E_INVALID, "d_global < d");
+
+    cudaError_t ce = cudaSetDevice(cfg->device);
+    if (ce != cudaSuccess) return fail(nullptr, PSMF_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+    psmf_engine* e = new (std::nothrow) psmf_engine();
+    if (!e) return fail(nullptr, PSMF_E_NOMEM, "host allocation failed");
+    e->cfg = *cfg;
+    e->cfg.d_global = dg;
+    e->R = cfg->r;
+    e->S = cfg->n_series;
+    e->d = cfg->d;
+    e->ntiles = (cfg->d + TILE - 1) / TILE;
+    e->esize = cfg->dtype == PSMF_F64 ? 8 : 4;
+    int sms = 0, maxsmem = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    e->num_sms = sms;
+
+    const int NG = ngroups_for(e->R);
+    // CTAs per series
+    int cps;
+    if (e->S > 1) {
+        cps = 1;
+    } else if (cfg->ctas > 0) {
+        cps = cfg->ctas;
+    } else {
+        int64_t want = e->ntiles / (2 * NG);
+        cps = (int)(want < 1 ? 1 : (want > sms ? sms : want));
+    }
+    if ((int64_t)cps > e->ntiles) cps = (int)e->ntiles;
+    LaunchShape shp;
+    for (;;) {
+        const int64_t tiles_per = (e->ntiles + cps - 1) / cps + 1;
+        e->dyn_smem = (size_t)tiles_per * TILE * sizeof(double);
+        ce = SHAPE[e->R](cfg->dtype, e->dyn_smem, &shp);
+        if (ce == cudaSuccess && shp.max_ctas_per_sm >= 1) break;
+        cudaGetLastError();
+        // residual buffer does not fit: use more CTAs if allowed
+        if (e->S == 1 && cfg->ctas <= 0 && cps < sms) {
+            cps = cps * 2 > sms ? sms : cps * 2;
+            continue;
+        }
+        free_engine(e);
+        return fail(nullptr, PSMF_E_NOMEM, "d too large: per-CTA residual buffer exceeds shared memory");
+    }
+    if (e->S == 1 && cps > 1 && cps > sms * shp.max_ctas_per_sm) cps = sms * shp.max_ctas_per_sm;
+    e->cps = cps;
+    e->threads = shp.threads;
+    e->cooperative = cps > 1;
+
+    const size_t cbytes = (size_t)e->S * e->ntiles * TILE * e->R * e->esize;
+    const int nsp = nstat_pad(e->R);
+#define CKC(call)                                                                                            \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            free_engine(e);                                                                                  \
+            return fail(nullptr, e__ == cudaErrorMemoryAllocation ? PSMF_E_NOMEM : PSMF_E_CUDA,              \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                                \
+        }                                                                                                    \
+    } while (0)
+    CKC(cudaMalloc(&e->C, cbytes));
+    CKC(cudaMemset(e->C, 0, cbytes));
+    CKC(cudaMalloc(&e->state, (size_t)e->S * st_size(e->R) * sizeof(double)));
+    CKC(cudaMemset(e->state, 0, (size_t)e->S * st_size(e->R) * sizeof(double)));
+    CKC(cudaMalloc(&e->partials, (size_t)2 * e->cps * nsp * sizeof(double)));
+    CKC(cudaMalloc(&e->bar, sizeof(unsigned long long)));
+    CKC(cudaMalloc(&e->status, sizeof(long long)));
+    CKC(cudaMemset(e->status, 0xFF, sizeof(long long)));
+#undef CKC
+    *out = e;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_destroy(psmf_handle h) {
+    if (!h) return PSMF_E_INVALID;
+    cudaSetDevice(h->cfg.device);
+    free_engine(h);
+    return PSMF_OK;
+}
+
+static int copy_small(psmf_engine* h, bool set, double* user, int off, int n, cudaStream_t st) {
+    if (!user) return PSMF_OK;
+    const size_t pitch = (size_t)st_size(h->R) * sizeof(double);
+    double* eng = h->state + off;
+    if (set)
+        CK(h, cudaMemcpy2DAsync(eng, pitch, user, n * sizeof(double), n * sizeof(double), h->S, cudaMemcpyDeviceToDevice, st));
+    else
+        CK(h, cudaMemcpy2DAsync(user, n * sizeof(double), eng, pitch, n * sizeof(double), h->S, cudaMemcpyDeviceToDevice, st));
+    return PSMF_OK;
+}
+
+static int state_io(psmf_engine* h, bool set, void* C, double* V, double* P, double* x, double* Q, double* rho,
+                    double* lambda, double* theta, cudaStream_t st) {
+    if (!h) return PSMF_E_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int R = h->R;
+    if (C) {
+        const int64_t total = (int64_t)h->S * h->ntiles * TILE * R;
+        const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+        if (h->cfg.dtype == PSMF_F64) {
+            if (set) pack_C<double><<<blocks, 256, 0, st>>>((const double*)C, (double*)h->C, h->d, R, h->ntiles, total);
+            else unpack_C<double><<<blocks, 256, 0, st>>>((const double*)h->C, (double*)C, h->d, R, h->ntiles, total);
+        } else {
+            if (set) pack_C<float><<<blocks, 256, 0, st>>>((const float*)C, (float*)h->C, h->d, R, h->ntiles, total);
+            else unpack_C<float><<<blocks, 256, 0, st>>>((const float*)h->C, (float*)C, h->d, R, h->ntiles, total);
+        }
+        CK(h, cudaGetLastError());
+    }
+    int rc;
+    if ((rc = copy_small(h, set, x, st_x(R), R, st))) return rc;
+    if ((rc = copy_small(h, set, P, st_P(R), R * R, st))) return rc;
+    if ((rc = copy_small(h, set, V, st_V(R), R * R, st))) return rc;
+    if ((rc = copy_small(h, set, Q, st_Q(R), R * R, st))) return rc;
+    if ((rc = copy_small(h, set, theta, st_theta(R), R, st))) return rc;
+    if ((rc = copy_small(h, set, rho, st_rho(R), 1, st))) return rc;
+    if ((rc = copy_small(h, set, lambda, st_lam(R), 1, st))) return rc;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_set_state(psmf_handle h, const void* C, const double* V, const double* P, const double* x,
+                              const double* Q, const double* rho, const double* lambda, const double* theta, void* stream) {
+    return state_io(h, true, const_cast<void*>(C), const_cast<double*>(V), const_cast<double*>(P), const_cast<double*>(x),
+                    const_cast<double*>(Q), const_cast<double*>(rho), const_cast<double*>(lambda),
+                    const_cast<double*>(theta), (cudaStream_t)stream);
+}
+
+extern "C" int psmf_get_state(psmf_handle h, void* C, double* V, double* P, double* x, double* Q, double* rho,
+                              double* lambda, double* theta, void* stream) {
+    return state_io(h, false, C, V, P, x, Q, rho, lambda, theta, (cudaStream_t)stream);
+}
+
+extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k0, void* stream) {
+    if (!h || !io) return PSMF_E_INVALID;
+    if (n_steps < 1) return fail(h, PSMF_E_INVALID, "n_steps must be >= 1");
+    if (!io->Y) return fail(h, PSMF_E_INVALID, "Y is NULL");
+    if (io->ldy < h->d) return fail(h, PSMF_E_INVALID, "ldy < d");
+    if (io->M && io->ldm < h->d) return fail(h, PSMF_E_INVALID, "ldm < d");
+    if (io->Yrec_out && io->ldrec < h->d) return fail(h, PSMF_E_INVALID, "ldrec < d");
+    if (h->cfg.dynamics == PSMF_DYN_EXTERNAL) {
+        if (n_steps != 1) return fail(h, PSMF_E_INVALID, "PSMF_DYN_EXTERNAL runs one step per call");
+        if (!io->xbar_ext || (!io->F_ext && !(h->cfg.flags & PSMF_SIMPLIFIED)))
+            return fail(h, PSMF_E_INVALID, "PSMF_DYN_EXTERNAL needs xbar_ext and F_ext");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(h, cudaSetDevice(h->cfg.device));
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.C = h->C;
+    p.c_series_stride = h->ntiles * TILE * h->R;
+    p.state = h->state;
+    p.Y = io->Y; p.ldy = io->ldy; p.ysst = io->y_series_stride;
+    p.M = io->M; p.ldm = io->ldm; p.msst = io->m_series_stride;
+    p.X_out = io->X_out;
+    p.Yrec = io->Yrec_out; p.ldrec = io->ldrec; p.recsst = io->rec_series_stride;
+    p.scal_out = io->scal_out;
+    p.xbar_ext = io->xbar_ext; p.F_ext = io->F_ext;
+    p.partials = h->partials;
+    p.bar = h->bar;
+    p.status = h->status;
+    p.d = h->d; p.d_global = h->cfg.d_global;
+    p.n_steps = n_steps; p.k0 = k0;
+    p.n_series = h->S; p.cps = h->cps;
+    p.flags = h->cfg.flags; p.dynamics = h->cfg.dynamics;
+    p.alpha = h->cfg.alpha; p.beta = h->cfg.beta;
+    p.world = 1; p.rank = 0;
+    CK(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned long long), st));
+    CK(h, cudaMemsetAsync(h->status, 0xFF, sizeof(long long), st));
+    const int grid = h->S * h->cps;
+    CK(h, LAUNCH[h->R](p, h->cfg.dtype, grid, h->dyn_smem, st, h->cooperative));
+    h->launches_last = 1;
+    h->last_stream = st;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_status(psmf_handle h, int64_t* first_bad_step) {
+    if (!h) return PSMF_E_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->last_stream));
+    long long v = -1;
+    CK(h, cudaMemcpy(&v, h->status, sizeof(v), cudaMemcpyDeviceToHost));
+    if (first_bad_step) *first_bad_step = (int64_t)v;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* smem_bytes, int32_t* launches) {
+    if (!h) return PSMF_E_INVALID;
+    if (ctas) *ctas = h->cps;
+    if (threads) *threads = h->threads;
+    if (smem_bytes) *smem_bytes = (int32_t)h->dyn_smem;
+    if (launches) *launches = h->launches_last;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_mailbox_export(psmf_handle h, void* ipc_handle_64B) {
+    (void)ipc_handle_64B;
+    return fail(h, PSMF_E_INVALID, "mailbox exchange not built yet");
+}
+extern "C" int psmf_mailbox_connect(psmf_handle h, const void* all_ipc_handles, int32_t n) {
+    (void)all_ipc_handles; (void)n;
+    return fail(h, PSMF_E_INVALID, "mailbox exchange not built yet");
+}

@@ -1,0 +1,112 @@
+// Shared definitions for the PSMF / rPSMF filter kernels (sm_100a).
+//
+// Data layout in HBM
+//   C      tiled structure-of-arrays: rows are grouped in tiles of 32; inside a tile the layout is
+//          [r][32] (column-major), i.e. element (i, j) lives at
+//              tile(i) * (R*32) + j*32 + (i & 31).
+//          A warp that maps lane -> row reads column j of a tile as one 256-byte coalesced request,
+//          and a tile is one contiguous R*256-byte block (bulk-copy friendly).
+//   Y, M   time-major (T, ld): the d values of one time step are contiguous.
+//   small  per series: [x R][P R*R][V R*R][Q R*R][theta R][rho][lambda] float64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace psmf {
+
+constexpr int TILE = 32;
+constexpr int NSCAL = 8;
+constexpr int MAXR = 16;
+constexpr int MAX_PEERS = 8;
+
+// flags (mirror include/psmf_b200.h)
+constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16;
+constexpr int DYN_IDENTITY = 0, DYN_COS = 1, DYN_EXTERNAL = 3;
+
+// ---- compile-time work split ---------------------------------------------------------------------
+// The upper triangle of the r x r Gram matrix (r(r+1)/2 fp64 accumulators) does not fit one thread's
+// registers at r = 16, so a 32-row tile is processed by NSPLIT warps ("roles"); role q owns Gram rows
+// j in [split_begin(q), split_begin(q+1)) and therefore needs columns j >= split_begin(q) of C.
+// Role 0 additionally owns y_hat, e, b, s, q1, q0, n_obs.
+__host__ __device__ constexpr int nsplit_for(int R) { return R <= 6 ? 1 : (R <= 10 ? 2 : 4); }
+__host__ __device__ constexpr int ngroups_for(int R) { return R <= 6 ? 8 : (R <= 10 ? 6 : 3); }
+__host__ __device__ constexpr int ngram(int R) { return R * (R + 1) / 2; }
+__host__ __device__ constexpr int nstat(int R) { return ngram(R) + R + 4; }
+__host__ __device__ constexpr int nstat_pad(int R) { return (nstat(R) + 7) / 8 * 8; }
+// packed index of Gram entry (j, j) in row-major upper-triangular order
+__host__ __device__ constexpr int gram_off(int R, int j) { return j * R - j * (j - 1) / 2; }
+
+__host__ __device__ constexpr int split_begin(int R, int NS, int q) {
+    if (q <= 0) return 0;
+    if (q >= NS) return R;
+    const int total = ngram(R) + 3 * R;     // role 0 carries ~3R extra FMAs per row (update, y_hat, b)
+    int acc = 3 * R;
+    int j = 0;
+    for (int role = 0; role < q; ++role) {
+        const int target = (total * (role + 1) + NS - 1) / NS;
+        const int start = j;
+        while (j < R) {
+            const int later = NS - 1 - role;
+            if (R - j <= later) break;                 // keep at least one Gram row for every later role
+            if (j > start && acc >= target) break;
+            acc += R - j;
+            ++j;
+        }
+    }
+    return j;
+}
+
+// small-state layout (doubles per series)
+__host__ __device__ constexpr int st_x(int R) { return 0; }
+__host__ __device__ constexpr int st_P(int R) { return R; }
+__host__ __device__ constexpr int st_V(int R) { return R + R * R; }
+__host__ __device__ constexpr int st_Q(int R) { return R + 2 * R * R; }
+__host__ __device__ constexpr int st_theta(int R) { return R + 3 * R * R; }
+__host__ __device__ constexpr int st_rho(int R) { return 2 * R + 3 * R * R; }
+__host__ __device__ constexpr int st_lam(int R) { return 2 * R + 3 * R * R + 1; }
+__host__ __device__ constexpr int st_size(int R) { return 2 * R + 3 * R * R + 2; }
+
+struct KParams {
+    void* C;                  // tiled, per series stride c_series_stride elements
+    int64_t c_series_stride;
+    double* state;            // n_series * st_size(R)
+    const void* Y; int64_t ldy; int64_t ysst;
+    const uint8_t* M; int64_t ldm; int64_t msst;
+    double* X_out;
+    void* Yrec; int64_t ldrec; int64_t recsst;
+    double* scal_out;
+    const double* xbar_ext; const double* F_ext;
+    double* partials;         // [2][ctas][nstat_pad]
+    unsigned long long* bar;  // grid barrier counter (monotonic within a launch)
+    long long* status;        // first bad step or -1
+    int64_t d, d_global;
+    int64_t n_steps, k0;
+    int32_t n_series, cps;    // CTAs per series
+    int32_t flags, dynamics;
+    double alpha, beta;
+    // multi-GPU stats exchange
+    int32_t world, rank;
+    double* mbox_local;                    // [2][world][nstat_pad] + flags
+    double* mbox_peer[MAX_PEERS];
+    unsigned long long* flag_local;        // [2][world]
+    unsigned long long* flag_peer[MAX_PEERS];
+    unsigned long long step_base;
+};
+
+struct LaunchShape {
+    int threads;
+    int static_smem;
+    int max_ctas_per_sm;   // with the given dynamic smem
+};
+
+// per-R entry points, one translation unit each (psmf_filter_inst.cu compiled with -DPSMF_R=n)
+typedef cudaError_t (*launch_fn)(const KParams&, int dtype, int grid, size_t dyn_smem, cudaStream_t, bool cooperative);
+typedef cudaError_t (*shape_fn)(int dtype, size_t dyn_smem, LaunchShape*);
+
+}  // namespace psmf
+
+#define PSMF_DECLARE_R(n)                                                                                   \
+    namespace psmf {                                                                                        \
+    cudaError_t launch_filter_r##n(const KParams&, int, int, size_t, cudaStream_t, bool);                   \
+    cudaError_t shape_filter_r##n(int, size_t, LaunchShape*);                                               \
+    }

@@ -1,0 +1,259 @@
+"""GPU parity tests: the CUDA filter (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerances: fp64 1e-9 norm-wise per quantity (max|delta| / max|ref|), fp32 storage 1e-4
+(BASELINE.json north_star); integer mask handling is exercised through exact zero / non-zero
+patterns (a missing row must not move C when y is zero-filled).
+"""
+
+import numpy as np
+import pytest
+
+from conftest import impute_case, load_golden, relerr
+from oracle import psmf_oracle as po
+from synth import impute_init, make_problem
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _engine_run(d, r, Y, M, C0, x0, init, robust, ctas=0, dtype=None, chunks=None, **kw):
+    torch = _torch()
+    from rpsmf_b200 import FilterEngine
+    dtype = dtype or torch.float64
+    eng = FilterEngine(d, r, dtype=dtype, robust=robust, ctas=ctas, **kw)
+    eng.set_state(C_=C0, V=init["V"], P=init["P"], x=x0, Q=init["Q"], rho=[init["rho"]], lam=[init["lam"]],
+                  theta=init.get("theta"))
+    dev = eng.device
+    Yd = torch.as_tensor(Y, dtype=dtype).to(dev)
+    Md = None if M is None else torch.as_tensor(M).to(dev)
+    T = Y.shape[0]
+    bounds = [0, T] if chunks is None else chunks
+    Xs, Yr, Sc = [], [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        out = eng.run(Yd[a:b], None if Md is None else Md[a:b], k0=1 + a, want_X=True, want_Yrec=True, want_scal=True)
+        assert eng.status() == -1
+        Xs.append(out["X"].cpu().numpy()); Yr.append(out["Yrec"].double().cpu().numpy()); Sc.append(out["scal"].cpu().numpy())
+    st = {k: (v.double().cpu().numpy() if v is not None else None) for k, v in eng.get_state().items()}
+    info = eng.launch_info()
+    eng.close()
+    return np.concatenate(Xs), np.concatenate(Yr), np.concatenate(Sc), st, info
+
+
+def _oracle_run(Y, M, C0, x0, init, cfg, k0=1):
+    st = po.OracleState(C0.copy(), x0.copy(), init["P"].copy(), init["V"].copy(), init["Q"].copy(), init["rho"],
+                        init["lam"], init.get("theta"))
+    return po.run(st, cfg, Y, None if M is None else M.astype(float), k0=k0)
+
+
+def _compare(res, ref, tol):
+    X, Yrec, scal, st, _ = res
+    ost, oX, oYrec, oscal = ref
+    assert relerr(X, oX) < tol
+    assert relerr(Yrec, oYrec) < tol
+    for k in range(8):
+        assert relerr(scal[:, k], oscal[:, k]) < tol, po.SCALAR_NAMES[k]
+    assert relerr(st["C"], ost.C) < tol
+    assert relerr(st["P"], ost.P) < tol
+    assert relerr(st["V"], ost.V) < tol
+    assert relerr(st["Q"], ost.Q) < tol
+    assert relerr(st["x"], ost.x) < tol
+    assert relerr(st["rho"], ost.rho) < tol
+    assert relerr(st["lam"], ost.lam) < tol
+
+
+@pytest.mark.parametrize("r", [1, 2, 3, 6, 7, 8, 10, 11, 13, 16])
+@pytest.mark.parametrize("robust", [True, False])
+def test_ranks_masked(r, robust):
+    d, T = 203, 40
+    Y, M, C0, x0 = make_problem(d, r, T, seed=r)
+    init = impute_init(r)
+    cfg = po.OracleConfig(robust=robust, c_update_transpose=robust)
+    res = _engine_run(d, r, Y, M, C0, x0, init, robust, c_update_transpose=robust)
+    _compare(res, _oracle_run(Y, M, C0, x0, init, cfg), TOL)
+
+
+@pytest.mark.parametrize("d,ctas", [(5, 0), (32, 0), (33, 1), (1000, 0), (1000, 3), (5000, 0), (5000, 37), (20011, 0)])
+def test_shapes_and_grids(d, ctas):
+    r, T = 16, 25
+    Y, M, C0, x0 = make_problem(d, r, T, seed=d)
+    init = impute_init(r)
+    res = _engine_run(d, r, Y, M, C0, x0, init, True, ctas=ctas)
+    _compare(res, _oracle_run(Y, M, C0, x0, init, po.OracleConfig(robust=True)), TOL)
+    if ctas:
+        assert res[4]["ctas"] == min(ctas, (d + 31) // 32)
+
+
+def test_unmasked_and_all_missing_steps():
+    d, r, T = 300, 10, 30
+    Y, M, C0, x0 = make_problem(d, r, T, seed=3)
+    init = impute_init(r)
+    # mask pointer NULL == all observed
+    Yfull, _, _, _ = make_problem(d, r, T, seed=3, missing=0.0)
+    res = _engine_run(d, r, Yfull, None, C0, x0, init, True)
+    _compare(res, _oracle_run(Yfull, None, C0, x0, init, po.OracleConfig(robust=True)), TOL)
+    # a few steps with every row missing, and rows that are always missing
+    M2 = M.copy(); M2[5] = 0; M2[17] = 0; M2[:, 7] = 0; M2[:, 299] = 0
+    Y2 = Y * M2
+    res = _engine_run(d, r, Y2, M2, C0, x0, init, True)
+    _compare(res, _oracle_run(Y2, M2, C0, x0, init, po.OracleConfig(robust=True)), TOL)
+    # exactness of the mask handling: a never-observed, zero-filled row of C must not move at all
+    assert np.array_equal(res[3]["C"][7], C0[7]) and np.array_equal(res[3]["C"][299], C0[299])
+
+
+def test_chunked_runs_carry_state():
+    d, r, T = 700, 16, 48
+    Y, M, C0, x0 = make_problem(d, r, T, seed=11)
+    init = impute_init(r)
+    one = _engine_run(d, r, Y, M, C0, x0, init, True)
+    many = _engine_run(d, r, Y, M, C0, x0, init, True, chunks=[0, 1, 2, 17, 48])
+    assert relerr(many[0], one[0]) < 1e-13
+    assert relerr(many[3]["C"], one[3]["C"]) < 1e-13
+    _compare(many, _oracle_run(Y, M, C0, x0, init, po.OracleConfig(robust=True)), TOL)
+
+
+def test_run_to_run_determinism():
+    d, r, T = 4000, 16, 20
+    Y, M, C0, x0 = make_problem(d, r, T, seed=5)
+    init = impute_init(r)
+    a = _engine_run(d, r, Y, M, C0, x0, init, True)
+    b = _engine_run(d, r, Y, M, C0, x0, init, True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3]["C"], b[3]["C"])
+
+
+def test_fp32_storage():
+    torch = _torch()
+    d, r, T = 600, 16, 40
+    Y, M, C0, x0 = make_problem(d, r, T, seed=21)
+    init = impute_init(r)
+    res = _engine_run(d, r, Y, M, C0, x0, init, True, dtype=torch.float32)
+    # the oracle sees the same fp32-rounded inputs
+    ref = _oracle_run(Y.astype(np.float32).astype(np.float64), M, C0.astype(np.float32).astype(np.float64), x0, init,
+                      po.OracleConfig(robust=True))
+    _compare(res, ref, 1e-4)
+
+
+def test_batched_series():
+    torch = _torch()
+    from rpsmf_b200 import FilterEngine
+    S, d, r, T = 7, 96, 8, 30
+    Y, M, C0, x0 = make_problem(d, r, T, seed=2, S=S)
+    init = impute_init(r)
+    eng = FilterEngine(d, r, n_series=S, robust=True)
+    eng.set_state(C_=C0, V=init["V"], P=init["P"], x=x0, Q=init["Q"], rho=[init["rho"]], lam=[init["lam"]])
+    out = eng.run(torch.as_tensor(Y).cuda(), torch.as_tensor(M).cuda(), want_X=True, want_Yrec=True, want_scal=True)
+    assert eng.status() == -1
+    st = eng.get_state()
+    for s in range(S):
+        ost, oX, oYrec, oscal = _oracle_run(Y[s], M[s], C0[s], x0[s], init, po.OracleConfig(robust=True))
+        assert relerr(out["X"][s].cpu().numpy(), oX) < TOL
+        assert relerr(out["Yrec"][s].cpu().numpy(), oYrec) < TOL
+        assert relerr(st["C"][s].cpu().numpy(), ost.C) < TOL
+        assert relerr(st["P"][s].cpu().numpy(), ost.P) < TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("tag,robust", [("psmf_full", False), ("rpsmf_full", True), ("rpsmf_scaled", True)])
+def test_pypsmf_fixture_cos_dynamics(tag, robust):
+    from rpsmf_b200 import _capi
+    g = load_golden("pypsmf_cases")
+    Y = g[tag + "_Y"]
+    T, d = Y.shape
+    C0 = g[tag + "_C0"]
+    r = C0.shape[1]
+    alpha = float(g[tag + "_alpha"]) if (tag + "_alpha") in g else 1.0
+    beta = float(g[tag + "_beta"]) if (tag + "_beta") in g else 1.0
+    init = dict(V=g[tag + "_V0"], P=g[tag + "_P0"], Q=g[tag + "_Q"], rho=float(g[tag + "_rho"]),
+                lam=float(g[tag + "_lam0"]) if robust else 0.0, theta=g[tag + "_theta0"])
+    X, Yrec, scal, st, _ = _engine_run(d, r, Y, None, C0, g[tag + "_mu0"], init, robust, dynamics=_capi.DYN_COS,
+                                       alpha=alpha, beta=beta)
+    assert relerr(Yrec, g[tag + "_ypred"]) < TOL
+    assert relerr(st["C"], g[tag + "_C"]) < TOL
+    assert relerr(st["x"], g[tag + "_mu"]) < TOL
+    assert relerr(st["P"], g[tag + "_P"]) < TOL
+    assert relerr(st["V"], g[tag + "_V"]) < TOL
+    if robust:
+        assert relerr(st["lam"], g[tag + "_lam_T"]) < TOL
+        assert relerr(st["rho"], g[tag + "_rho_T"]) < TOL
+
+
+@pytest.mark.parametrize("tag,robust", [("syn_psmf", False), ("syn_rpsmf", True)])
+def test_simplified_mode_fixture(tag, robust):
+    from rpsmf_b200 import _capi
+    g = load_golden("pypsmf_cases")
+    Y = g[tag + "_Y"]
+    T, d = Y.shape
+    C0 = g[tag + "_C0"]
+    r = C0.shape[1]
+    init = dict(V=g[tag + "_V0"], P=np.zeros((r, r)), Q=np.zeros((r, r)), rho=1.0, lam=1.8 if robust else 0.0,
+                theta=g[tag + "_thetas"][0])
+    X, Yrec, scal, st, _ = _engine_run(d, r, Y, None, C0, np.zeros(r), init, robust, dynamics=_capi.DYN_COS,
+                                       simplified=True)
+    assert relerr(st["C"], g[tag + "_Cs"][0]) < TOL
+    assert relerr(st["x"], g[tag + "_mus"][0]) < TOL
+
+
+def test_external_dynamics_stepwise():
+    """PSMF_DYN_EXTERNAL: the host supplies x_bar and a dense F for every step (arbitrary callables)."""
+    torch = _torch()
+    from rpsmf_b200 import FilterEngine, _capi
+    d, r, T = 150, 5, 12
+    Y, M, C0, x0 = make_problem(d, r, T, seed=9)
+    init = impute_init(r)
+    rng = np.random.RandomState(0)
+    A = np.eye(r) + 0.05 * rng.randn(r, r)
+    eng = FilterEngine(d, r, robust=True, dynamics=_capi.DYN_EXTERNAL)
+    eng.set_state(C_=C0, V=init["V"], P=init["P"], x=x0, Q=init["Q"], rho=[init["rho"]], lam=[init["lam"]])
+    st = po.OracleState(C0.copy(), x0.copy(), init["P"].copy(), init["V"].copy(), init["Q"].copy(), init["rho"], init["lam"])
+    cfg = po.OracleConfig(robust=True)
+    Yd, Md = torch.as_tensor(Y).cuda(), torch.as_tensor(M).cuda()
+    for t in range(T):
+        xbar = np.tanh(A @ st.x)
+        F = (1 - xbar ** 2)[:, None] * A
+        st, out = po.step(st, cfg, Y[t], M[t].astype(float), xbar_F=(xbar, F))
+        xg = eng.get_state(want_C=False)["x"].cpu().numpy()
+        xbar_g = np.tanh(A @ xg)
+        Fg = (1 - xbar_g ** 2)[:, None] * A
+        res = eng.run(Yd[t:t + 1], Md[t:t + 1], k0=t + 1, xbar=xbar_g, F=Fg)
+        assert relerr(res["X"][0].cpu().numpy(), st.x) < TOL
+    gs = eng.get_state()
+    assert relerr(gs["C"].cpu().numpy(), st.C) < TOL
+    assert relerr(gs["P"].cpu().numpy(), st.P) < TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["impute_pm25_30", "impute_pm10_head_20", "impute_sp500_head_30"])
+@pytest.mark.parametrize("method", ["rPSMF", "PSMF"])
+def test_impute_functions_against_reference_fixtures(name, method):
+    """The drop-in flat functions reproduce what the unmodified reference returned (and, for PM25, published)."""
+    from rpsmf_b200 import ProbabilisticSequentialMatrixFactorizer, robust_PSMF
+    g = load_golden(name)
+    c = impute_case(g)
+    r = c["r"]
+    d, n = c["Y"].shape
+    X = c["X0"].copy()
+    C = c["C0"].copy()
+    pre = "rep0_%s_" % method
+    Einit = float(g[pre + "Einit"])
+    V, Q, R, P = 2 * np.eye(r), 0.1 * np.eye(r), 10 * np.eye(d), np.eye(r)
+    if method == "rPSMF":
+        ep, ef, rt, ib = robust_PSMF(c["Y"], C, X, d, n, r, c["M"], c["Mmiss"], V, Q, R, P, 1.8, 2, c["Iter"], c["YorigInt"], Einit)
+    else:
+        ep, ef, rt, ib = ProbabilisticSequentialMatrixFactorizer(c["Y"], C, X, d, n, r, c["M"], c["Mmiss"], 0, V, Q, R, P, 2,
+                                                                 c["Iter"], c["YorigInt"], Einit)
+    assert np.array_equal(C, c["C0"])                      # C is not mutated (rPSMF.py:111 rebinds)
+    assert relerr(X, g[pre + "X_final"]) < TOL             # X is (rPSMF.py:104)
+    assert relerr(ep, g[pre + "Epred"]) < TOL
+    assert relerr(ef, g[pre + "Efull"]) < TOL
+    assert abs(ib - float(g[pre + "inside"])) < 1e-12
+    assert ep.shape == (1, c["Iter"] + 1) and rt.shape == (1, c["Iter"] + 1)
+    if (pre + "published") in g:
+        pub = g[pre + "published"]
+        assert abs(ep[0, -1] - pub[0]) / pub[0] < 1e-9
+        assert abs(ef[0, -1] - pub[1]) / pub[1] < 1e-9
+        assert abs(ib - pub[2]) < 1e-12
