@@ -138,7 +138,10 @@ def small_update(st: OracleState, cfg: OracleConfig, xbar, F, vx, vxt, a, S, d):
         omega = 1.0
     N = a + eta                                       # rPSMF.py:109
     if cfg.robust:
-        phi = (lam + q1 / (a + eta) + q0 / eta) / (lam + d)   # rPSMF.py:112-114
+        # rPSMF.py:112-114.  A step with every row missing has eta = 0 and the reference evaluates
+        # 0 * inf = NaN there (Ui = 1/diag(U), rPSMF.py:113); mirrored here with numpy semantics.
+        with np.errstate(divide="ignore", invalid="ignore"):
+            phi = float((lam + np.float64(q1) / (a + eta) + np.float64(q0) / np.float64(eta)) / (lam + d))
     else:
         phi = 1.0
     if cfg.simplified:

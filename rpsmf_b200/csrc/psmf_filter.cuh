@@ -74,10 +74,12 @@ __host__ __device__ constexpr int bfly_final(int n) {
     for (int i = 0; i < 5; ++i) n = (n + 1) / 2;
     return n;
 }
+// Entries with index >= lim are padding (odd counts are rounded up at every stage) and must not be stored.
 template <int N, int O, int NA>
-__device__ __forceinline__ void bfly(double (&v)[NA], int lane, int& base) {
+__device__ __forceinline__ void bfly(double (&v)[NA], int lane, int& base, int& lim) {
     constexpr int H = (N + 1) / 2;
     const bool up = (lane & O) != 0;
+    lim = min(lim, base + N);
 #pragma unroll
     for (int i = 0; i < H; ++i) {
         const double lo = v[i];
@@ -87,7 +89,7 @@ __device__ __forceinline__ void bfly(double (&v)[NA], int lane, int& base) {
         v[i] = keep + __shfl_xor_sync(FULL, send, O);
     }
     if (up) base += H;
-    if constexpr (O > 1) bfly<H, O / 2, NA>(v, lane, base);
+    if constexpr (O > 1) bfly<H, O / 2, NA>(v, lane, base, lim);
 }
 
 // ---- row pass of one role over the CTA's tiles ----------------------------------------------------
@@ -153,13 +155,13 @@ __device__ __forceinline__ void role_pass(const KParams& p, Smem<R>& sh, double*
         }
     }
 
-    int base = 0;
-    bfly<NACC, 16, NACC>(acc, lane, base);
+    int base = 0, lim = NACC;
+    bfly<NACC, 16, NACC>(acc, lane, base, lim);
     constexpr int NF = bfly_final(NACC);
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
         const int li = base + i;
-        if (li < NACC) {
+        if (li < lim) {
             int gi;
             if (Q == 0)
                 gi = li < NGR ? li : ngram(R) + (li - NGR);
@@ -263,7 +265,7 @@ __device__ void predict(const KParams& p, Smem<R>& sh, int lane, int64_t k, int 
     __syncwarp();
 }
 
-// Gauss-Jordan with partial pivoting on the R x (2R+1) augmented matrix [I + Pbar G | Pbar | b] (warp 0).
+// Gauss-Jordan with partial pivoting on the R x (2R+1) augmented matrix [I + Pbar G | Pbar | Pbar b] (warp 0).
 template <int R>
 __device__ void gauss_jordan(double (*aug)[2 * R + 2], int lane) {
     constexpr int NC = 2 * R + 1;
@@ -321,7 +323,12 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
             sh.aug[i][j] = acc;
             sh.aug[i][R + j] = sh.Pb[i * R + j];
         }
-        if (tid < R) sh.aug[tid][2 * R] = tot[NGm + tid];
+        if (tid < R) {                                   // right-hand side Pbar b: the solve then yields K b
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < R; ++k) acc = fma(sh.Pb[tid * R + k], tot[NGm + k], acc);
+            sh.aug[tid][2 * R] = acc;
+        }
     }
     __syncthreads();
     if (warp == 0) {

@@ -97,13 +97,25 @@ def test_unmasked_and_all_missing_steps():
     Yfull, _, _, _ = make_problem(d, r, T, seed=3, missing=0.0)
     res = _engine_run(d, r, Yfull, None, C0, x0, init, True)
     _compare(res, _oracle_run(Yfull, None, C0, x0, init, po.OracleConfig(robust=True)), TOL)
-    # a few steps with every row missing, and rows that are always missing
-    M2 = M.copy(); M2[5] = 0; M2[17] = 0; M2[:, 7] = 0; M2[:, 299] = 0
+    # rows that are always missing, and steps with a single observed row
+    M2 = M.copy(); M2[5] = 0; M2[5, 3] = 1; M2[17] = 0; M2[17, 298] = 1; M2[:, 7] = 0; M2[:, 299] = 0
     Y2 = Y * M2
     res = _engine_run(d, r, Y2, M2, C0, x0, init, True)
     _compare(res, _oracle_run(Y2, M2, C0, x0, init, po.OracleConfig(robust=True)), TOL)
     # exactness of the mask handling: a never-observed, zero-filled row of C must not move at all
     assert np.array_equal(res[3]["C"][7], C0[7]) and np.array_equal(res[3]["C"][299], C0[299])
+
+
+def test_all_rows_missing_step_stays_finite():
+    """The reference yields NaN on a step with every row missing (0 * inf at rPSMF.py:113-114); the CUDA
+    path defines q0/eta := 0 when q0 == 0, so such a step is a pure prediction step."""
+    d, r, T = 100, 6, 12
+    Y, M, C0, x0 = make_problem(d, r, T, seed=4)
+    M[6] = 0
+    Y = Y * M
+    X, Yrec, scal, st, _ = _engine_run(d, r, Y, M, C0, x0, impute_init(r), True)
+    assert np.isfinite(X).all() and np.isfinite(st["C"]).all() and np.isfinite(st["V"]).all()
+    assert np.array_equal(X[6], X[5])          # no observation: x_t = x_bar
 
 
 def test_chunked_runs_carry_state():
