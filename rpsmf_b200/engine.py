@@ -173,6 +173,57 @@ class FilterEngine:
             res = {k: v[0] for k, v in res.items()}
         return res
 
+    def run_host(self, Y_host, M_host=None, window=256, k0=1, want_X=True):
+        """Filter a long HOST-resident sequence: Y_host (T, d) pinned CPU tensor in the engine dtype, M_host
+        (T, d) uint8.  Windows of ``window`` steps are copied host->device on a side stream while the
+        previous window is being filtered (double buffering); returns X (T, r) on the host (pinned).
+        Single-series engines only."""
+        if self.S != 1:
+            raise ValueError("run_host supports single-series engines")
+        T, d = Y_host.shape[0], self.d
+        dev = self.device
+        if not hasattr(self, "_hb") or self._hb[0].shape[0] < window or self._hb[0].shape[1] != Y_host.shape[1]:
+            ld = Y_host.shape[1]
+            self._hb = [torch.empty((window, ld), dtype=self.dtype, device=dev) for _ in range(2)]
+            self._hm = [torch.empty((window, ld), dtype=torch.uint8, device=dev) for _ in range(2)] if M_host is not None else None
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._hx = torch.empty((2, window, self.r), dtype=torch.float64, device=dev)
+        Xh = torch.empty((T, self.r), dtype=torch.float64).pin_memory() if want_X else None
+        main = torch.cuda.current_stream(dev)
+        cs = self._copy_stream
+        nwin = (T + window - 1) // window
+        copied = [None, None]
+        done = [None, None]
+
+        def issue_copy(w):
+            a, b = w * window, min(T, (w + 1) * window)
+            slot = w & 1
+            if done[slot] is not None:
+                cs.wait_event(done[slot])          # the run that last read this slot has finished
+            with torch.cuda.stream(cs):
+                self._hb[slot][: b - a].copy_(Y_host[a:b], non_blocking=True)
+                if M_host is not None:
+                    self._hm[slot][: b - a].copy_(M_host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            copied[slot] = ev
+
+        issue_copy(0)
+        for w in range(nwin):
+            a, b = w * window, min(T, (w + 1) * window)
+            slot = w & 1
+            if w + 1 < nwin:
+                issue_copy(w + 1)
+            main.wait_event(copied[slot])
+            out = self.run(self._hb[slot][: b - a], None if M_host is None else self._hm[slot][: b - a], k0=k0 + a,
+                           want_X=False, X_out=self._hx[slot][: b - a].unsqueeze(0) if want_X else None)
+            if want_X:
+                Xh[a:b].copy_(self._hx[slot][: b - a], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            done[slot] = ev
+        return Xh
+
     def status(self):
         """Synchronise and return the first step with a non-finite N/omega/phi/x, or -1."""
         bad = C.c_int64(-1)
