@@ -83,7 +83,7 @@ typedef struct psmf_config {
     int32_t world_size; /* GPUs sharing ONE series by rows (1 = no exchange)                       */
     int32_t rank;
     int32_t ctas;       /* CTAs per series, 0 = auto                                                */
-    int32_t reserved;
+    int32_t kernel;     /* 0 = auto, 1 = direct-load kernel, 2 = TMA-staged kernel (error if not eligible)  */
     double  alpha;      /* V scale (rpsmf.py:45-51), 1.0 unless use_scaling                        */
     double  beta;       /* P scale                                                                  */
 } psmf_config;
@@ -126,9 +126,11 @@ int  psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k0, voi
  * *first_bad_step = -1 if every step produced finite N/omega/phi, else the first offending step.    */
 int  psmf_status(psmf_handle h, int64_t* first_bad_step);
 
-/* introspection used by bench.py / tests: CTAs per series, threads per CTA, dynamic smem bytes,
- * kernels launched by the last psmf_run.                                                            */
+/* introspection used by bench.py / tests, describing the last psmf_run: CTAs per series, threads per CTA,
+ * dynamic smem bytes, kernels launched, which kernel ran (1 direct-load, 2 TMA-staged) and its
+ * shared-memory chunk slots (0 for kernel 1).                                                        */
 int  psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* smem_bytes, int32_t* launches);
+int  psmf_launch_info2(psmf_handle h, int32_t* kernel, int32_t* nslot, int32_t* resident);
 
 /* multi-GPU row sharding (world_size > 1): NVLink mailbox for the per-step statistics exchange.
  * Each rank exports an IPC handle of its mailbox (64 bytes), gathers all ranks' handles through the

@@ -22,7 +22,7 @@ SCAL_NAMES = ("a", "eta", "N", "omega", "phi", "sSe", "lam", "rho")
 # every symbol include/psmf_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = (
     "psmf_create", "psmf_destroy", "psmf_last_error", "psmf_version", "psmf_set_state", "psmf_get_state",
-    "psmf_run", "psmf_status", "psmf_launch_info", "psmf_mailbox_export", "psmf_mailbox_connect",
+    "psmf_run", "psmf_status", "psmf_launch_info", "psmf_launch_info2", "psmf_mailbox_export", "psmf_mailbox_connect",
 )
 
 
@@ -30,7 +30,7 @@ class PsmfConfig(C.Structure):
     _fields_ = [
         ("d", C.c_int64), ("d_global", C.c_int64), ("r", C.c_int32), ("n_series", C.c_int32),
         ("dtype", C.c_int32), ("flags", C.c_int32), ("dynamics", C.c_int32), ("device", C.c_int32),
-        ("world_size", C.c_int32), ("rank", C.c_int32), ("ctas", C.c_int32), ("reserved", C.c_int32),
+        ("world_size", C.c_int32), ("rank", C.c_int32), ("ctas", C.c_int32), ("kernel", C.c_int32),
         ("alpha", C.c_double), ("beta", C.c_double),
     ]
 
@@ -75,6 +75,7 @@ def lib():
     L.psmf_run.argtypes = [vp, C.POINTER(PsmfIO), i64, i64, vp]
     L.psmf_status.argtypes = [vp, C.POINTER(i64)]
     L.psmf_launch_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.psmf_launch_info2.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.psmf_mailbox_export.argtypes = [vp, vp]
     L.psmf_mailbox_connect.argtypes = [vp, vp, i32]
     for name in EXPORTS:

@@ -1,6 +1,7 @@
 // C ABI of the B200-native PSMF / rPSMF filter (include/psmf_b200.h).
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 #include <new>
 #include <string>
 
@@ -18,6 +19,14 @@ static const launch_fn LAUNCH[MAXR + 1] = {
     nullptr,           launch_filter_r1,  launch_filter_r2,  launch_filter_r3,  launch_filter_r4,  launch_filter_r5,
     launch_filter_r6,  launch_filter_r7,  launch_filter_r8,  launch_filter_r9,  launch_filter_r10, launch_filter_r11,
     launch_filter_r12, launch_filter_r13, launch_filter_r14, launch_filter_r15, launch_filter_r16};
+static const launch_fn LAUNCH_S[MAXR + 1] = {
+    nullptr,           launch_stream_r1,  launch_stream_r2,  launch_stream_r3,  launch_stream_r4,  launch_stream_r5,
+    launch_stream_r6,  launch_stream_r7,  launch_stream_r8,  launch_stream_r9,  launch_stream_r10, launch_stream_r11,
+    launch_stream_r12, launch_stream_r13, launch_stream_r14, launch_stream_r15, launch_stream_r16};
+static const shape_fn SHAPE_S[MAXR + 1] = {
+    nullptr,          shape_stream_r1,  shape_stream_r2,  shape_stream_r3,  shape_stream_r4,  shape_stream_r5,
+    shape_stream_r6,  shape_stream_r7,  shape_stream_r8,  shape_stream_r9,  shape_stream_r10, shape_stream_r11,
+    shape_stream_r12, shape_stream_r13, shape_stream_r14, shape_stream_r15, shape_stream_r16};
 static const shape_fn SHAPE[MAXR + 1] = {
     nullptr,          shape_filter_r1,  shape_filter_r2,  shape_filter_r3,  shape_filter_r4,  shape_filter_r5,
     shape_filter_r6,  shape_filter_r7,  shape_filter_r8,  shape_filter_r9,  shape_filter_r10, shape_filter_r11,
@@ -65,6 +74,11 @@ struct psmf_engine {
     int cps = 1, threads = 0, launches_last = 0, num_sms = 0;
     size_t dyn_smem = 0;
     bool cooperative = false;
+    // TMA-staged kernel configuration (cps2 == 0: not available for this shape)
+    int cps2 = 0, threads2 = 0, nslot = 0;
+    size_t dyn_smem2 = 0;
+    bool resident2 = false;
+    int last_kernel = 0;
     cudaStream_t last_stream = nullptr;
     std::string err;
 };
@@ -164,6 +178,46 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     e->threads = shp.threads;
     e->cooperative = cps > 1;
 
+    // ---- TMA-staged kernel: slots of (2 * groups) tiles + y/m slices, residual buffer behind them ----
+    if (cfg->kernel != 1 && e->d % 16 == 0) {
+        const int NG2 = e->R <= 6 ? 8 : (e->R <= 10 ? 6 : 3);
+        const int TS = 2 * NG2;
+        auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
+        const size_t slot = r128((size_t)TS * e->R * TILE * e->esize) + r128((size_t)TS * TILE * e->esize) + r128((size_t)TS * TILE);
+        int cps2;
+        if (e->S > 1) cps2 = 1;
+        else if (cfg->ctas > 0) cps2 = cfg->ctas;
+        else {
+            int64_t want = e->ntiles / TS;
+            cps2 = (int)(want < 1 ? 1 : (want > sms ? sms : want));
+        }
+        if ((int64_t)cps2 > e->ntiles) cps2 = (int)e->ntiles;
+        if (e->S == 1 && cps2 > sms) cps2 = sms;                       // one CTA per SM (cooperative launch)
+        LaunchShape shp2;
+        if (SHAPE_S[e->R](cfg->dtype, 0, &shp2) == cudaSuccess) {
+            const int64_t tiles_max = (e->ntiles + cps2 - 1) / cps2;
+            const int64_t nchunks_max = (tiles_max + TS - 1) / TS;
+            const size_t ebuf = (size_t)tiles_max * TILE * sizeof(double);
+            const int64_t avail = (int64_t)maxsmem - shp2.static_smem - (int64_t)ebuf - 256;
+            int64_t nslot = avail > 0 ? avail / (int64_t)slot : 0;
+            if (nslot > nchunks_max) nslot = nchunks_max;
+            if (nslot > 64) nslot = 64;
+            if (nslot >= (nchunks_max >= 2 ? 2 : 1)) {
+                e->cps2 = cps2;
+                e->nslot = (int)nslot;
+                e->dyn_smem2 = (size_t)nslot * slot + ebuf;
+                e->threads2 = shp2.threads;
+                e->resident2 = nchunks_max <= nslot;
+                if (SHAPE_S[e->R](cfg->dtype, e->dyn_smem2, &shp2) != cudaSuccess || shp2.max_ctas_per_sm < 1) e->cps2 = 0;
+            }
+        }
+        cudaGetLastError();
+    }
+    if (cfg->kernel == 2 && e->cps2 == 0) {
+        free_engine(e);
+        return fail(nullptr, PSMF_E_INVALID, "TMA-staged kernel not available for this shape (needs d % 16 == 0 and room for 2 slots)");
+    }
+
     const size_t cbytes = (size_t)e->S * e->ntiles * TILE * e->R * e->esize;
     const int nsp = nstat_pad(e->R);
 #define CKC(call)                                                                                            \
@@ -179,7 +233,7 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     CKC(cudaMemset(e->C, 0, cbytes));
     CKC(cudaMalloc(&e->state, (size_t)e->S * st_size(e->R) * sizeof(double)));
     CKC(cudaMemset(e->state, 0, (size_t)e->S * st_size(e->R) * sizeof(double)));
-    CKC(cudaMalloc(&e->partials, (size_t)2 * e->cps * nsp * sizeof(double)));
+    CKC(cudaMalloc(&e->partials, (size_t)2 * (e->cps > e->cps2 ? e->cps : e->cps2) * nsp * sizeof(double)));
     CKC(cudaMalloc(&e->bar, sizeof(unsigned long long)));
     CKC(cudaMalloc(&e->status, sizeof(long long)));
     CKC(cudaMemset(e->status, 0xFF, sizeof(long long)));
@@ -282,8 +336,25 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     p.world = 1; p.rank = 0;
     CK(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned long long), st));
     CK(h, cudaMemsetAsync(h->status, 0xFF, sizeof(long long), st));
-    const int grid = h->S * h->cps;
-    CK(h, LAUNCH[h->R](p, h->cfg.dtype, grid, h->dyn_smem, st, h->cooperative));
+    // the TMA-staged kernel needs 16-byte aligned rows of Y / M (bulk copies)
+    const size_t es = h->esize;
+    bool aligned = h->cps2 > 0 && ((uintptr_t)io->Y % 16 == 0) && ((size_t)io->ldy * es % 16 == 0) &&
+                   ((size_t)io->y_series_stride * es % 16 == 0);
+    if (io->M) aligned = aligned && ((uintptr_t)io->M % 16 == 0) && (io->ldm % 16 == 0) && (io->m_series_stride % 16 == 0);
+    const int NG2 = h->R <= 6 ? 8 : (h->R <= 10 ? 6 : 3);
+    bool use2 = aligned && h->cfg.dynamics != PSMF_DYN_EXTERNAL &&
+                (h->cfg.kernel == 2 || (h->cfg.kernel == 0 && h->ntiles >= 8 * NG2));
+    if (h->cfg.kernel == 2 && !use2)
+        return fail(h, PSMF_E_INVALID, "kernel=2 requested but Y/M are not 16-byte aligned (or dynamics is external)");
+    if (use2) {
+        p.cps = h->cps2;
+        p.nslot = h->nslot;
+        CK(h, LAUNCH_S[h->R](p, h->cfg.dtype, h->S * h->cps2, h->dyn_smem2, st, h->cps2 > 1));
+        h->last_kernel = 2;
+    } else {
+        CK(h, LAUNCH[h->R](p, h->cfg.dtype, h->S * h->cps, h->dyn_smem, st, h->cooperative));
+        h->last_kernel = 1;
+    }
     h->launches_last = 1;
     h->last_stream = st;
     return PSMF_OK;
@@ -301,10 +372,19 @@ extern "C" int psmf_status(psmf_handle h, int64_t* first_bad_step) {
 
 extern "C" int psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* smem_bytes, int32_t* launches) {
     if (!h) return PSMF_E_INVALID;
-    if (ctas) *ctas = h->cps;
-    if (threads) *threads = h->threads;
-    if (smem_bytes) *smem_bytes = (int32_t)h->dyn_smem;
+    const bool k2 = h->last_kernel == 2;
+    if (ctas) *ctas = k2 ? h->cps2 : h->cps;
+    if (threads) *threads = k2 ? h->threads2 : h->threads;
+    if (smem_bytes) *smem_bytes = (int32_t)(k2 ? h->dyn_smem2 : h->dyn_smem);
     if (launches) *launches = h->launches_last;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_launch_info2(psmf_handle h, int32_t* kernel, int32_t* nslot, int32_t* resident) {
+    if (!h) return PSMF_E_INVALID;
+    if (kernel) *kernel = h->last_kernel;
+    if (nslot) *nslot = h->last_kernel == 2 ? h->nslot : 0;
+    if (resident) *resident = h->last_kernel == 2 && h->resident2 ? 1 : 0;
     return PSMF_OK;
 }
 

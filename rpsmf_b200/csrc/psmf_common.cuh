@@ -91,6 +91,9 @@ struct KParams {
     unsigned long long* flag_local;        // [2][world]
     unsigned long long* flag_peer[MAX_PEERS];
     unsigned long long step_base;
+    // streaming kernel
+    int32_t nslot;            // shared-memory chunk slots per CTA
+    int32_t pad0;
 };
 
 struct LaunchShape {
@@ -109,4 +112,6 @@ typedef cudaError_t (*shape_fn)(int dtype, size_t dyn_smem, LaunchShape*);
     namespace psmf {                                                                                        \
     cudaError_t launch_filter_r##n(const KParams&, int, int, size_t, cudaStream_t, bool);                   \
     cudaError_t shape_filter_r##n(int, size_t, LaunchShape*);                                               \
+    cudaError_t launch_stream_r##n(const KParams&, int, int, size_t, cudaStream_t, bool);                   \
+    cudaError_t shape_stream_r##n(int, size_t, LaunchShape*);                                               \
     }

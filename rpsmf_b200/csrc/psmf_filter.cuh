@@ -51,15 +51,19 @@ __device__ __forceinline__ void red_release_gpu(unsigned long long* p, unsigned 
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// barrier 0 over the first `n` threads of the CTA (n == blockDim.x: plain __syncthreads; the streaming
+// kernel excludes its producer warp)
+__device__ __forceinline__ void sync_n(int n) { asm volatile("bar.sync 0, %0;" ::"r"(n) : "memory"); }
+
 // All CTAs of the grid are co-resident (cooperative launch).  `target` grows monotonically.
-__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
-    __syncthreads();
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target, int nthr) {
+    sync_n(nthr);
     if (threadIdx.x == 0) {
         red_release_gpu(bar, 1ULL);
         while (ld_acquire_gpu(bar) < target) {
         }
     }
-    __syncthreads();
+    sync_n(nthr);
 }
 
 __device__ __forceinline__ double warp_allsum(double v) {
@@ -306,13 +310,13 @@ __device__ void gauss_jordan(double (*aug)[2 * R + 2], int lane) {
 // ---- r x r part of the step (rPSMF.py:102-115,133-135), identical on every CTA ---------------------
 template <int R>
 __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, int warp, int series, int64_t t,
-                             bool writer) {
+                             bool writer, int nthr) {
     constexpr int NGm = ngram(R);
     const bool simp = (p.flags & F_SIMPLIFIED) != 0;
     const bool robust = (p.flags & F_ROBUST) != 0;
     const double* tot = sh.tot;
     if (!simp) {
-        for (int idx = tid; idx < R * R; idx += blockDim.x) {
+        for (int idx = tid; idx < R * R; idx += nthr) {
             const int i = idx / R, j = idx % R;
             double acc = (i == j) ? 1.0 : 0.0;
 #pragma unroll
@@ -330,7 +334,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
             sh.aug[tid][2 * R] = acc;
         }
     }
-    __syncthreads();
+    sync_n(nthr);
     if (warp == 0) {
         if (!simp) gauss_jordan<R>(sh.aug, lane);     // aug[:, R:2R] = K, aug[:, 2R] = K b
         const double a = sh.a, rho = sh.rho, lam = sh.lam;
@@ -394,7 +398,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         __syncwarp();
         if (t + 1 < p.n_steps) predict<R>(p, sh, lane, p.k0 + t + 1, series);
     }
-    __syncthreads();
+    sync_n(nthr);
 }
 
 template <int R, typename T>
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(nsplit_for(R) * ngroups_for(R) * 32, 1) psmf_f
             const int parity = (int)(t & 1);
             double* mine = p.partials + ((size_t)parity * gridDim.x + blockIdx.x) * NSP;
             if (tid < NST) mine[tid] = sh.part[tid];
-            grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1));
+            grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), blockDim.x);
             const double* basep = p.partials + ((size_t)parity * gridDim.x + (size_t)series * p.cps) * NSP;
             if (tid < NST) {
                 // fixed summation order: 4 interleaved chains over the CTAs, combined as (s0+s1)+(s2+s3)
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(nsplit_for(R) * ngroups_for(R) * 32, 1) psmf_f
             if (tid < NST) sh.tot[tid] = sh.part[tid];
         }
         __syncthreads();
-        small_update<R>(p, sh, tid, lane, warp, series, t, writer);
+        small_update<R>(p, sh, tid, lane, warp, series, t, writer, blockDim.x);
     }
 
     dispatch_flush<R, T, 0>(role, sh, ebuf, Cs, tb, te, group, lane);

@@ -1,0 +1,409 @@
+// TMA-staged PSMF / rPSMF filter kernel (sm_100a): the large-d path.
+//
+// Same step as psmf_filter.cuh, but C never travels through registers from global memory.  A producer
+// warp moves contiguous CHUNKS of the tiled C (plus the matching slices of y_t and m_t) between HBM and a
+// ring of shared-memory slots with bulk asynchronous copies (cp.async.bulk, the 1-D TMA path: UBLKCP in
+// SASS) that complete on mbarriers; the consumer warps read tiles from shared memory, apply the pending
+// rank-1 update, accumulate the statistics, write the updated tile back into the slot, and the producer
+// bulk-stores it to HBM.  Two regimes, chosen per CTA:
+//
+//   streaming  (chunks of the CTA > slots): the slots form a ring; per step every chunk is loaded once and
+//              stored once -> HBM traffic = 2 d r s_C + d (s_y + 1) bytes per step.  While the consumers
+//              sit in the reduction / grid barrier / r x r solve, the producer already fills the ring
+//              with the first chunks of the next step.
+//   resident   (chunks <= slots): C is loaded once, stays in shared memory for the whole launch and is
+//              stored once at the end; only y_t / m_t stream.
+//
+// Requirements checked by the host (else the direct-load kernel of psmf_filter.cuh is used): 16-byte
+// aligned Y / M base pointers and time strides, d a multiple of 16.
+#pragma once
+#include "psmf_filter.cuh"
+
+namespace psmf {
+
+constexpr int MAXSLOT = 64;
+
+__host__ __device__ constexpr int s_nsplit(int R) { return R <= 6 ? 1 : (R <= 10 ? 2 : 5); }
+__host__ __device__ constexpr int s_ngroups(int R) { return R <= 6 ? 8 : (R <= 10 ? 6 : 3); }
+__host__ __device__ constexpr int s_tiles_per_chunk(int R) { return 2 * s_ngroups(R); }
+__host__ __device__ constexpr int s_threads(int R) { return (s_nsplit(R) * s_ngroups(R) + 1) * 32; }
+
+// Gram rows owned by role q: boundaries minimising max(2*accumulators + 2*columns) per role, then FMAs
+// (computed offline; role 0 also carries y_hat / e / b / s / q1 / q0 / n_obs).
+__host__ __device__ constexpr int s_split_begin(int R, int q) {
+    const int NS = s_nsplit(R);
+    if (q <= 0) return 0;
+    if (q >= NS) return R;
+    if (NS == 2) return R <= 8 ? 1 : 2;
+    // NS == 5, R in 11..16
+    switch (R) {
+        case 11: { const int b[6] = {0, 1, 2, 3, 4, 11}; return b[q]; }
+        case 12: { const int b[6] = {0, 1, 2, 3, 5, 12}; return b[q]; }
+        case 13: { const int b[6] = {0, 1, 2, 3, 6, 13}; return b[q]; }
+        case 14: { const int b[6] = {0, 1, 2, 3, 6, 14}; return b[q]; }
+        case 15: { const int b[6] = {0, 1, 2, 4, 7, 15}; return b[q]; }
+        default: { const int b[6] = {0, 1, 3, 5, 8, 16}; return b[q]; }
+    }
+}
+
+__host__ __device__ constexpr size_t round128(size_t x) { return (x + 127) / 128 * 128; }
+template <int R, typename T>
+struct SlotLayout {
+    static constexpr int TS = s_tiles_per_chunk(R);
+    static constexpr size_t TILE_BYTES = (size_t)R * TILE * sizeof(T);
+    static constexpr size_t CB = round128(TS * TILE_BYTES);
+    static constexpr size_t YB = round128((size_t)TS * TILE * sizeof(T));
+    static constexpr size_t MB = round128((size_t)TS * TILE);
+    static constexpr size_t SLOT = CB + YB + MB;
+};
+
+// ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- consumer: one role over all chunks of one pass ----------------------------------------------------
+// FLUSH: apply the pending rank-1 update only (the pass after the last step).
+template <int R, int Q, typename T, bool FLUSH>
+__device__ __forceinline__ void s_role_pass(const KParams& p, Smem<R>& sh, double* __restrict__ ebuf,
+                                            unsigned char* __restrict__ slots, uint64_t* full, uint64_t* done,
+                                            T* __restrict__ Yrec_t, bool masked, int tb, int nt, int nslot, int64_t pass,
+                                            int group, int lane) {
+    using L = SlotLayout<R, T>;
+    constexpr int NS = s_nsplit(R), NG = s_ngroups(R), NSP = nstat_pad(R), TS = L::TS;
+    constexpr int JB = s_split_begin(R, Q), JE = s_split_begin(R, Q + 1);
+    constexpr int NGR = gram_off(R, JE) - gram_off(R, JB);
+    constexpr int NACC = FLUSH ? 1 : NGR + (Q == 0 ? R + 4 : 0);
+    const double a = sh.a, rho = sh.rho;
+    const int nchunks = (nt + TS - 1) / TS;
+    const bool streaming = nchunks > nslot;
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+    for (int k = 0; k < nchunks; ++k) {
+        const int64_t kk = pass * nchunks + k;
+        const int slot = streaming ? (int)(kk % nslot) : k;
+        const uint32_t parity = (uint32_t)((streaming ? kk / nslot : pass) & 1);
+        unsigned char* sb = slots + (size_t)slot * L::SLOT;
+        mbar_wait(&full[slot], parity);
+        const int ntc = min(TS, nt - k * TS);
+        for (int i = group; i < ntc; i += NG) {
+            const int tl = k * TS + i;                                   // tile index inside the CTA
+            const int64_t row = (int64_t)(tb + tl) * TILE + lane;
+            const int rl = tl * TILE + lane;
+            T* ct = reinterpret_cast<T*>(sb) + (size_t)i * (R * TILE) + lane;
+            if constexpr (FLUSH) {
+                const double ep = ebuf[rl];
+#pragma unroll
+                for (int j = JB; j < JE; ++j) ct[j * TILE] = (T)fma(ep, sh.g[j], (double)ct[j * TILE]);
+            } else {
+            double c[R];
+#pragma unroll
+            for (int j = JB; j < R; ++j) c[j] = (double)ct[j * TILE];
+            const double ep = ebuf[rl];
+            const bool inb = row < p.d;
+            bool mi = inb;
+            if (masked && inb) mi = (sb + L::CB + L::YB)[i * TILE + lane] != 0;
+            double yi = 0.0;
+            if (Q == 0 && inb) yi = (double)reinterpret_cast<const T*>(sb + L::CB)[i * TILE + lane];
+            if (NS > 1) named_bar_sync(1 + group, NS * 32);
+#pragma unroll
+            for (int j = JB; j < R; ++j) c[j] = fma(ep, sh.g[j], c[j]);      // rPSMF.py:111 (previous step)
+#pragma unroll
+            for (int j = JB; j < JE; ++j) ct[j * TILE] = (T)c[j];
+            const double w = 1.0 / ((mi ? rho : 0.0) + a);                    // rPSMF.py:92,98,32
+            const double mw = mi ? w : 0.0;
+#pragma unroll
+            for (int j = JB; j < JE; ++j) {
+                const double cw = c[j] * mw;
+#pragma unroll
+                for (int k2 = j; k2 < R; ++k2) {
+                    const int idx = gram_off(R, j) - gram_off(R, JB) + (k2 - j);
+                    acc[idx] = fma(cw, c[k2], acc[idx]);                      // G = CM' Ri CM, rPSMF.py:35
+                }
+            }
+            if (Q == 0) {
+                double yh = 0.0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) yh = fma(c[j], sh.xb[j], yh);     // rPSMF.py:89
+                const double e = yi - (mi ? yh : 0.0);                        // rPSMF.py:101
+                ebuf[rl] = e;
+                if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
+                const double ew = e * mw;
+#pragma unroll
+                for (int j = 0; j < R; ++j) acc[NGR + j] = fma(ew, c[j], acc[NGR + j]);
+                const double e2 = e * e;
+                acc[NGR + R + 0] = fma(inb ? w : 0.0, e2, acc[NGR + R + 0]);
+                acc[NGR + R + 1] += mi ? e2 : 0.0;
+                acc[NGR + R + 2] += mi ? 0.0 : e2;
+                acc[NGR + R + 3] += mi ? 1.0 : 0.0;
+            }
+            }  // !FLUSH
+        }
+        // this warp is done with the slot: make its generic-proxy writes visible to the bulk store
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[slot]);
+    }
+    if (FLUSH) return;
+
+    int base = 0, lim = NACC;
+    bfly<NACC, 16, NACC>(acc, lane, base, lim);
+    constexpr int NF = bfly_final(NACC);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        const int li = base + i;
+        if (li < lim) {
+            int gi;
+            if (Q == 0)
+                gi = li < NGR ? li : ngram(R) + (li - NGR);
+            else
+                gi = gram_off(R, JB) + li;
+            sh.red[group * NSP + gi] = acc[i];
+        }
+    }
+}
+
+template <int R, typename T, bool FLUSH, int Q>
+__device__ __forceinline__ void s_dispatch(int role, const KParams& p, Smem<R>& sh, double* ebuf, unsigned char* slots,
+                                           uint64_t* full, uint64_t* done, T* Yrec_t, bool masked, int tb, int nt,
+                                           int nslot, int64_t pass, int group, int lane) {
+    if (role == Q) {
+        s_role_pass<R, Q, T, FLUSH>(p, sh, ebuf, slots, full, done, Yrec_t, masked, tb, nt, nslot, pass, group, lane);
+        return;
+    }
+    if constexpr (Q + 1 < s_nsplit(R))
+        s_dispatch<R, T, FLUSH, Q + 1>(role, p, sh, ebuf, slots, full, done, Yrec_t, masked, tb, nt, nslot, pass, group, lane);
+}
+
+// ---- producer: one thread drives all bulk copies of the CTA -------------------------------------------
+template <int R, typename T>
+__device__ void s_producer(const KParams& p, unsigned char* slots, uint64_t* full, uint64_t* done, T* Cs, int series,
+                           int tb, int nt, int nslot) {
+    using L = SlotLayout<R, T>;
+    constexpr int TS = L::TS;
+    const int nchunks = (nt + TS - 1) / TS;
+    const bool streaming = nchunks > nslot;
+    const int64_t npass = p.n_steps + 1;
+    const bool masked = p.M != nullptr;
+    int64_t kk = 0;
+    for (int64_t pass = 0; pass < npass; ++pass) {
+        const bool last = pass == p.n_steps;
+        const T* Yt = last ? nullptr : reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst + pass * p.ldy;
+        const uint8_t* Mt = (last || !masked) ? nullptr : p.M + (int64_t)series * p.msst + pass * p.ldm;
+        for (int k = 0; k < nchunks; ++k, ++kk) {
+            const int slot = streaming ? (int)(kk % nslot) : k;
+            const int64_t use = streaming ? kk / nslot : pass;
+            unsigned char* sb = slots + (size_t)slot * L::SLOT;
+            if (use > 0) {
+                mbar_wait(&done[slot], (uint32_t)((use - 1) & 1));        // consumers released the previous occupant
+                if (streaming) {
+                    const int pk = (int)((kk - nslot) % nchunks);
+                    const int ptiles = min(TS, nt - pk * TS);
+                    bulk_store(Cs + (size_t)(tb + pk * TS) * (R * TILE), sb, (uint32_t)(ptiles * L::TILE_BYTES));
+                    bulk_commit();
+                    bulk_wait_read<0>();                                   // slot may be overwritten
+                    // the chunk loaded below was stored (nchunks - nslot) groups ago: make sure that store has
+                    // fully completed before reading it back
+                    if (nchunks - nslot >= 2) bulk_wait<2>(); else bulk_wait<0>();
+                }
+            }
+            const int ntc = min(TS, nt - k * TS);
+            const int64_t row0 = (int64_t)(tb + k * TS) * TILE;
+            int64_t vrows = p.d - row0;
+            vrows = vrows < 0 ? 0 : (vrows > (int64_t)ntc * TILE ? (int64_t)ntc * TILE : vrows);
+            const bool loadC = streaming || pass == 0;
+            const uint32_t cbytes = loadC ? (uint32_t)(ntc * L::TILE_BYTES) : 0u;
+            const uint32_t ybytes = (Yt != nullptr) ? (uint32_t)(vrows * sizeof(T)) : 0u;
+            const uint32_t mbytes = (Mt != nullptr) ? (uint32_t)vrows : 0u;
+            const uint32_t tx = cbytes + ybytes + mbytes;
+            if (tx == 0) {
+                mbar_arrive(&full[slot]);
+            } else {
+                mbar_arrive_expect_tx(&full[slot], tx);
+                if (cbytes) bulk_load(sb, Cs + (size_t)(tb + k * TS) * (R * TILE), cbytes, &full[slot]);
+                if (ybytes) bulk_load(sb + L::CB, Yt + row0, ybytes, &full[slot]);
+                if (mbytes) bulk_load(sb + L::CB + L::YB, Mt + row0, mbytes, &full[slot]);
+            }
+        }
+    }
+    // drain: store what is still only in shared memory
+    if (streaming) {
+        for (int64_t j = kk - nslot; j < kk; ++j) {
+            const int slot = (int)(j % nslot);
+            mbar_wait(&done[slot], (uint32_t)((j / nslot) & 1));
+            const int pk = (int)(j % nchunks);
+            const int ptiles = min(TS, nt - pk * TS);
+            bulk_store(Cs + (size_t)(tb + pk * TS) * (R * TILE), slots + (size_t)slot * L::SLOT, (uint32_t)(ptiles * L::TILE_BYTES));
+            bulk_commit();
+        }
+    } else {
+        for (int k = 0; k < nchunks; ++k) {
+            mbar_wait(&done[k], (uint32_t)((npass - 1) & 1));
+            const int ptiles = min(TS, nt - k * TS);
+            bulk_store(Cs + (size_t)(tb + k * TS) * (R * TILE), slots + (size_t)k * L::SLOT, (uint32_t)(ptiles * L::TILE_BYTES));
+            bulk_commit();
+        }
+    }
+    bulk_wait<0>();
+}
+
+template <int R, typename T>
+__global__ void __launch_bounds__(s_threads(R), 1) psmf_stream_kernel(const KParams p) {
+    using L = SlotLayout<R, T>;
+    constexpr int NS = s_nsplit(R), NG = s_ngroups(R), NSP = nstat_pad(R), NST = nstat(R);
+    constexpr int NCW = NS * NG, NCT = NCW * 32;
+    extern __shared__ __align__(128) unsigned char dyn_smem_s[];
+    __shared__ Smem<R> sh;
+    __shared__ __align__(8) uint64_t full[MAXSLOT];
+    __shared__ __align__(8) uint64_t done[MAXSLOT];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int series = blockIdx.x / p.cps;
+    const int part = blockIdx.x % p.cps;
+    const int ntiles = (int)((p.d + TILE - 1) / TILE);
+    const int tb = (int)((int64_t)ntiles * part / p.cps);
+    const int te = (int)((int64_t)ntiles * (part + 1) / p.cps);
+    const int nt = te - tb;
+    const bool writer = part == 0;
+    const int nslot = p.nslot;
+
+    unsigned char* slots = dyn_smem_s;
+    double* ebuf = reinterpret_cast<double*>(dyn_smem_s + (size_t)nslot * L::SLOT);
+    T* Cs = reinterpret_cast<T*>(p.C) + (int64_t)series * p.c_series_stride;
+    double* stg = p.state + (int64_t)series * st_size(R);
+
+    if (tid == 0) {
+        for (int s = 0; s < nslot; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&done[s], NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < R * R; i += blockDim.x) {
+        sh.P[i] = stg[st_P(R) + i];
+        sh.V[i] = stg[st_V(R) + i];
+        sh.Q[i] = stg[st_Q(R) + i];
+    }
+    if (tid < R) {
+        sh.x[tid] = stg[st_x(R) + tid];
+        sh.th[tid] = stg[st_theta(R) + tid];
+        sh.g[tid] = 0.0;
+    }
+    if (tid == 0) {
+        sh.rho = stg[st_rho(R)];
+        sh.lam = stg[st_lam(R)];
+    }
+    for (int i = tid; i < nt * TILE; i += blockDim.x) ebuf[i] = 0.0;
+    __syncthreads();
+
+    if (warp == NCW) {                       // ---- producer warp ----
+        if (lane == 0) s_producer<R, T>(p, slots, full, done, Cs, series, tb, nt, nslot);
+        return;
+    }
+
+    // ---- consumer warps ----
+    const int group = warp / NS;
+    const int role = ((warp % NS) + group) % NS;
+    const bool masked = p.M != nullptr;
+    if (warp == 0) predict<R>(p, sh, lane, p.k0, series);
+    sync_n(NCT);
+
+    for (int64_t t = 0; t < p.n_steps; ++t) {
+        T* Yrec_t = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + t * p.ldrec : nullptr;
+        s_dispatch<R, T, false, 0>(role, p, sh, ebuf, slots, full, done, Yrec_t, masked, tb, nt, nslot, t, group, lane);
+        sync_n(NCT);
+        if (tid < NST) {
+            double s = 0.0;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) s += sh.red[g * NSP + tid];
+            sh.part[tid] = s;
+        }
+        if (p.cps > 1) {
+            const int parity = (int)(t & 1);
+            double* mine = p.partials + ((size_t)parity * gridDim.x + blockIdx.x) * NSP;
+            if (tid < NST) mine[tid] = sh.part[tid];
+            grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), NCT);
+            const double* basep = p.partials + ((size_t)parity * gridDim.x + (size_t)series * p.cps) * NSP;
+            if (tid < NST) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int c = 0;
+                for (; c + 3 < p.cps; c += 4) {
+                    s0 += __ldcg(basep + (size_t)(c + 0) * NSP + tid);
+                    s1 += __ldcg(basep + (size_t)(c + 1) * NSP + tid);
+                    s2 += __ldcg(basep + (size_t)(c + 2) * NSP + tid);
+                    s3 += __ldcg(basep + (size_t)(c + 3) * NSP + tid);
+                }
+                for (; c < p.cps; ++c) s0 += __ldcg(basep + (size_t)c * NSP + tid);
+                sh.tot[tid] = (s0 + s1) + (s2 + s3);
+            }
+        } else {
+            if (tid < NST) sh.tot[tid] = sh.part[tid];
+        }
+        sync_n(NCT);
+        small_update<R>(p, sh, tid, lane, warp, series, t, writer, NCT);
+    }
+
+    // flush pass: pending rank-1 update of the last step
+    s_dispatch<R, T, true, 0>(role, p, sh, ebuf, slots, full, done, (T*)nullptr, masked, tb, nt, nslot, p.n_steps, group, lane);
+    if (writer) {
+        for (int i = tid; i < R * R; i += NCT) {
+            stg[st_P(R) + i] = sh.P[i];
+            stg[st_V(R) + i] = sh.V[i];
+            stg[st_Q(R) + i] = sh.Q[i];
+        }
+        if (tid < R) stg[st_x(R) + tid] = sh.x[tid];
+        if (tid == 0) {
+            stg[st_rho(R)] = sh.rho;
+            stg[st_lam(R)] = sh.lam;
+        }
+    }
+}
+
+}  // namespace psmf

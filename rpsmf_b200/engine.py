@@ -29,7 +29,7 @@ class FilterEngine:
 
     def __init__(self, d, r, *, n_series=1, dtype=torch.float64, robust=True, simplified=False,
                  c_update_transpose=True, fixed_lambda=False, dynamics=_capi.DYN_IDENTITY, alpha=1.0, beta=1.0,
-                 device=None, d_global=None, world_size=1, rank=0, ctas=0):
+                 device=None, d_global=None, world_size=1, rank=0, ctas=0, kernel=0):
         if not torch.cuda.is_available():
             raise RuntimeError("rpsmf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         if dtype not in (torch.float64, torch.float32):
@@ -46,7 +46,7 @@ class FilterEngine:
         cfg = _capi.PsmfConfig(
             d=self.d, d_global=int(d_global or d), r=self.r, n_series=self.S,
             dtype=_capi.F64 if dtype == torch.float64 else _capi.F32, flags=flags, dynamics=int(dynamics),
-            device=self.device.index, world_size=int(world_size), rank=int(rank), ctas=int(ctas), reserved=0,
+            device=self.device.index, world_size=int(world_size), rank=int(rank), ctas=int(ctas), kernel=int(kernel),
             alpha=float(alpha), beta=float(beta))
         self._L = _capi.lib()
         self._h = C.c_void_p()
@@ -233,4 +233,7 @@ class FilterEngine:
     def launch_info(self):
         a, b, c, dd = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         self._ck(self._L.psmf_launch_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(dd)))
-        return dict(ctas=a.value, threads=b.value, smem_bytes=c.value, launches=dd.value)
+        k, ns, res = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self._L.psmf_launch_info2(self._h, C.byref(k), C.byref(ns), C.byref(res)))
+        return dict(ctas=a.value, threads=b.value, smem_bytes=c.value, launches=dd.value,
+                    kernel={0: "none", 1: "direct", 2: "tma"}[k.value], nslot=ns.value, resident=bool(res.value))

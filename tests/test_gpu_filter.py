@@ -89,6 +89,57 @@ def test_shapes_and_grids(d, ctas):
         assert res[4]["ctas"] == min(ctas, (d + 31) // 32)
 
 
+@pytest.mark.parametrize("d,ctas,r,resident", [
+    (3840, 1, 16, False),      # one CTA, 20 chunks through a ring of slots (streaming)
+    (3856, 1, 16, False),      # last tile half-filled (d % 32 == 16)
+    (3840, 3, 16, None),
+    (1600, 2, 16, True),       # everything fits the slots: C stays in shared memory
+    (20000, 0, 16, None),
+    (60000, 0, 16, None),
+    (9600, 1, 8, None),
+    (9600, 2, 10, None),
+    (4800, 1, 3, None),
+    (12000, 0, 12, None),
+])
+def test_tma_kernel(d, ctas, r, resident):
+    T = 12
+    Y, M, C0, x0 = make_problem(d, r, T, seed=d + r)
+    init = impute_init(r)
+    res = _engine_run(d, r, Y, M, C0, x0, init, True, ctas=ctas, kernel=2)
+    assert res[4]["kernel"] == "tma"
+    if resident is not None:
+        assert res[4]["resident"] == resident
+    _compare(res, _oracle_run(Y, M, C0, x0, init, po.OracleConfig(robust=True)), TOL)
+
+
+def test_tma_kernel_variants():
+    torch = _torch()
+    d, r, T = 7680, 16, 14
+    Y, M, C0, x0 = make_problem(d, r, T, seed=77)
+    init = impute_init(r)
+    ref = _oracle_run(Y, M, C0, x0, init, po.OracleConfig(robust=True))
+    # several launches: the pending rank-1 update is flushed at the end of every launch
+    res = _engine_run(d, r, Y, M, C0, x0, init, True, ctas=2, kernel=2, chunks=[0, 1, 5, 14])
+    assert res[4]["kernel"] == "tma"
+    _compare(res, ref, TOL)
+    # no mask pointer
+    Yf, _, _, _ = make_problem(d, r, T, seed=77, missing=0.0)
+    res = _engine_run(d, r, Yf, None, C0, x0, init, True, ctas=2, kernel=2)
+    _compare(res, _oracle_run(Yf, None, C0, x0, init, po.OracleConfig(robust=True)), TOL)
+    # PSMF (non-robust) and fp32 storage
+    res = _engine_run(d, r, Y, M, C0, x0, init, False, ctas=2, kernel=2, c_update_transpose=False)
+    _compare(res, _oracle_run(Y, M, C0, x0, init, po.OracleConfig(robust=False, c_update_transpose=False)), TOL)
+    res = _engine_run(d, r, Y, M, C0, x0, init, True, ctas=2, kernel=2, dtype=torch.float32)
+    ref32 = _oracle_run(Y.astype(np.float32).astype(np.float64), M, C0.astype(np.float32).astype(np.float64), x0, init,
+                        po.OracleConfig(robust=True))
+    _compare(res, ref32, 1e-4)
+    # both kernels agree to rounding
+    a = _engine_run(d, r, Y, M, C0, x0, init, True, kernel=1)
+    b = _engine_run(d, r, Y, M, C0, x0, init, True, kernel=2)
+    assert a[4]["kernel"] == "direct" and b[4]["kernel"] == "tma"
+    assert relerr(a[0], b[0]) < 1e-12 and relerr(a[3]["C"], b[3]["C"]) < 1e-12
+
+
 def test_unmasked_and_all_missing_steps():
     d, r, T = 300, 10, 30
     Y, M, C0, x0 = make_problem(d, r, T, seed=3)
