@@ -202,6 +202,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    torch.cuda.profiler.start()          # ncu --profile-from-start off: skip the data generation kernels
     for i in range(args.warmup):
         one_step(i)
     barrier()
@@ -215,6 +216,7 @@ def main():
         evs[i + 1].record()
     barrier()
     clocks = sampler.stop()
+    torch.cuda.profiler.stop()
     bad = eng.status()
     total_ms = evs[0].elapsed_time(evs[-1])
     per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]

@@ -132,6 +132,11 @@ int  psmf_status(psmf_handle h, int64_t* first_bad_step);
 int  psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* smem_bytes, int32_t* launches);
 int  psmf_launch_info2(psmf_handle h, int32_t* kernel, int32_t* nslot, int32_t* resident);
 
+/* debug: record globaltimer stamps of CTA 0 for the first `steps` filter steps of every following psmf_run
+ * into dev_buf ([steps][8] uint64: pass start, pass end, after CTA sync, before grid barrier, after grid
+ * barrier, statistics reduced, step end, after the r x r solve).  dev_buf == NULL disables.           */
+int  psmf_set_trace(psmf_handle h, uint64_t* dev_buf, int32_t steps);
+
 /* multi-GPU row sharding (world_size > 1): NVLink mailbox for the per-step statistics exchange.
  * Each rank exports an IPC handle of its mailbox (64 bytes), gathers all ranks' handles through the
  * host-side process group, and connects.                                                            */

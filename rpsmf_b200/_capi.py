@@ -22,7 +22,7 @@ SCAL_NAMES = ("a", "eta", "N", "omega", "phi", "sSe", "lam", "rho")
 # every symbol include/psmf_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = (
     "psmf_create", "psmf_destroy", "psmf_last_error", "psmf_version", "psmf_set_state", "psmf_get_state",
-    "psmf_run", "psmf_status", "psmf_launch_info", "psmf_launch_info2", "psmf_mailbox_export", "psmf_mailbox_connect",
+    "psmf_run", "psmf_status", "psmf_launch_info", "psmf_launch_info2", "psmf_set_trace", "psmf_mailbox_export", "psmf_mailbox_connect",
 )
 
 
@@ -76,6 +76,7 @@ def lib():
     L.psmf_status.argtypes = [vp, C.POINTER(i64)]
     L.psmf_launch_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.psmf_launch_info2.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.psmf_set_trace.argtypes = [vp, vp, i32]
     L.psmf_mailbox_export.argtypes = [vp, vp]
     L.psmf_mailbox_connect.argtypes = [vp, vp, i32]
     for name in EXPORTS:

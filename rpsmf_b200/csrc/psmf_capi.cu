@@ -79,6 +79,8 @@ struct psmf_engine {
     size_t dyn_smem2 = 0;
     bool resident2 = false;
     int last_kernel = 0;
+    unsigned long long* trace = nullptr;
+    int trace_steps = 0;
     cudaStream_t last_stream = nullptr;
     std::string err;
 };
@@ -233,7 +235,11 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     CKC(cudaMemset(e->C, 0, cbytes));
     CKC(cudaMalloc(&e->state, (size_t)e->S * st_size(e->R) * sizeof(double)));
     CKC(cudaMemset(e->state, 0, (size_t)e->S * st_size(e->R) * sizeof(double)));
-    CKC(cudaMalloc(&e->partials, (size_t)2 * (e->cps > e->cps2 ? e->cps : e->cps2) * nsp * sizeof(double)));
+    {
+        const int cmax = e->cps > e->cps2 ? e->cps : e->cps2;
+        const size_t pstr = (size_t)((cmax + 7) & ~7) + 1;            // transposed partials + totals (grid_reduce)
+        CKC(cudaMalloc(&e->partials, (size_t)2 * nsp * (pstr > 17 ? pstr : 17) * sizeof(double)));
+    }
     CKC(cudaMalloc(&e->bar, sizeof(unsigned long long)));
     CKC(cudaMalloc(&e->status, sizeof(long long)));
     CKC(cudaMemset(e->status, 0xFF, sizeof(long long)));
@@ -334,6 +340,7 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     p.flags = h->cfg.flags; p.dynamics = h->cfg.dynamics;
     p.alpha = h->cfg.alpha; p.beta = h->cfg.beta;
     p.world = 1; p.rank = 0;
+    p.trace = h->trace; p.trace_steps = h->trace_steps;
     CK(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned long long), st));
     CK(h, cudaMemsetAsync(h->status, 0xFF, sizeof(long long), st));
     // the TMA-staged kernel needs 16-byte aligned rows of Y / M (bulk copies)
@@ -385,6 +392,13 @@ extern "C" int psmf_launch_info2(psmf_handle h, int32_t* kernel, int32_t* nslot,
     if (kernel) *kernel = h->last_kernel;
     if (nslot) *nslot = h->last_kernel == 2 ? h->nslot : 0;
     if (resident) *resident = h->last_kernel == 2 && h->resident2 ? 1 : 0;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_set_trace(psmf_handle h, uint64_t* dev_buf, int32_t steps) {
+    if (!h) return PSMF_E_INVALID;
+    h->trace = (unsigned long long*)dev_buf;
+    h->trace_steps = dev_buf ? steps : 0;
     return PSMF_OK;
 }
 

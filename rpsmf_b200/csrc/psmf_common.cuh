@@ -93,7 +93,8 @@ struct KParams {
     unsigned long long step_base;
     // streaming kernel
     int32_t nslot;            // shared-memory chunk slots per CTA
-    int32_t pad0;
+    int32_t trace_steps;      // debug: number of steps recorded in `trace`
+    unsigned long long* trace; // debug: [trace_steps][8] globaltimer stamps of CTA 0 (or nullptr)
 };
 
 struct LaunchShape {

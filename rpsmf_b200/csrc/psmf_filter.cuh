@@ -32,11 +32,14 @@ struct Smem {
     double g[R];        // rank-1 direction of the previous step
     double th[R];
     double P[R * R], V[R * R], Q[R * R], Pb[R * R];
-    double aug[R][2 * R + 2];
+    double aug[2][R][2 * R + 2];   // double-buffered augmented matrix of the r x r solve
     double tot[NSP];
     double part[NSP];
-    double red[NG * NSP];
+    double red[NG * NSP];          // per row-group partial statistics
     double a, rho, lam;
+    double w1, w0;                 // 1/(rho + a), 1/a : the only two values of w_i (rPSMF.py:92,98,32)
+    double sc[8];                  // omega, eta, N, phi, sSe, alpha*phi, beta*omega
+    int perm[R];                   // pivot row of elimination step k
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -64,6 +67,15 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
         }
     }
     sync_n(nthr);
+}
+
+// debug phase stamps (CTA 0, thread 0): enabled when KParams.trace != nullptr
+__device__ __forceinline__ void stamp(const KParams& p, int64_t t, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && t < p.trace_steps) {
+        unsigned long long v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+        p.trace[t * 8 + slot] = v;
+    }
 }
 
 __device__ __forceinline__ double warp_allsum(double v) {
@@ -105,7 +117,7 @@ __device__ __forceinline__ void role_pass(const KParams& p, Smem<R>& sh, double*
     constexpr int JB = split_begin(R, NS, Q), JE = split_begin(R, NS, Q + 1);
     constexpr int NGR = gram_off(R, JE) - gram_off(R, JB);
     constexpr int NACC = NGR + (Q == 0 ? R + 4 : 0);
-    const double a = sh.a, rho = sh.rho;
+    const double w1 = sh.w1, w0 = sh.w0;
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
@@ -130,8 +142,8 @@ __device__ __forceinline__ void role_pass(const KParams& p, Smem<R>& sh, double*
         for (int j = JB; j < R; ++j) c[j] = fma(ep, sh.g[j], c[j]);          // rPSMF.py:111 (previous step)
 #pragma unroll
         for (int j = JB; j < JE; ++j) ct[j * TILE] = (T)c[j];
-        const double w = 1.0 / ((mi ? rho : 0.0) + a);                        // rPSMF.py:92,98,32
-        const double mw = mi ? w : 0.0;
+        const double w = mi ? w1 : w0;                                        // rPSMF.py:92,98,32
+        const double mw = mi ? w1 : 0.0;
 #pragma unroll
         for (int j = JB; j < JE; ++j) {
             const double cw = c[j] * mw;
@@ -142,9 +154,10 @@ __device__ __forceinline__ void role_pass(const KParams& p, Smem<R>& sh, double*
             }
         }
         if (Q == 0) {
-            double yh = 0.0;
+            double yh4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int j = 0; j < R; ++j) yh = fma(c[j], sh.xb[j], yh);         // rPSMF.py:89
+            for (int j = 0; j < R; ++j) yh4[j & 3] = fma(c[j], sh.xb[j], yh4[j & 3]);   // rPSMF.py:89
+            const double yh = (yh4[0] + yh4[1]) + (yh4[2] + yh4[3]);
             const double e = yi - (mi ? yh : 0.0);                            // rPSMF.py:101
             ebuf[rl] = e;
             if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
@@ -210,108 +223,118 @@ __device__ __forceinline__ void dispatch_flush(int role, Smem<R>& sh, const doub
     if constexpr (Q + 1 < nsplit_for(R)) dispatch_flush<R, T, Q + 1>(role, sh, ebuf, Cs, tb, te, group, lane);
 }
 
-// ---- predict half: x_bar = f(x), P_bar = F P F' + Q, V x_bar, a (warp 0) ---------------------------
+// ---- predict half: x_bar = f(x), P_bar = F P F' + Q, V x_bar, a (all `nthr` threads; ends with a barrier) ----
 template <int R>
-__device__ void predict(const KParams& p, Smem<R>& sh, int lane, int64_t k, int series) {
+__device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, int series, int nthr) {
     const bool simp = (p.flags & F_SIMPLIFIED) != 0;
-    if (lane < R) {
+    const int lane = tid & 31;
+    if (tid < R) {
         double xb, fd = 1.0;
         if (p.dynamics == DYN_COS) {                                          // synthetic_psmf.py:105-106
-            const double arg = __dadd_rn(__dmul_rn(__dmul_rn(6.283185307179586, sh.th[lane]), (double)k), sh.x[lane]);
+            const double arg = __dadd_rn(__dmul_rn(__dmul_rn(6.283185307179586, sh.th[tid]), (double)k), sh.x[tid]);
             xb = cos(arg);
             fd = -sin(arg);
         } else if (p.dynamics == DYN_EXTERNAL) {
-            xb = p.xbar_ext[(int64_t)series * R + lane];
+            xb = p.xbar_ext[(int64_t)series * R + tid];
         } else {
-            xb = sh.x[lane];                                                  // rPSMF.py:86
+            xb = sh.x[tid];                                                   // rPSMF.py:86
         }
-        sh.xb[lane] = xb;
-        sh.fd[lane] = fd;
+        sh.xb[tid] = xb;
+        sh.fd[tid] = fd;
     }
-    __syncwarp();
-    double av = 0.0;
-    if (lane < R) {
-        const int j = lane;
-        if (simp) {                                                           // synthetic_psmf.py:83-84
+    sync_n(nthr);
+    if (tid >= nthr - 32) {
+        // last warp: V x_bar, V' x_bar, a = x_bar' V x_bar and the two possible row weights
+        double v = 0.0;
+        if (lane < 2 * R) {
+            const int j = lane < R ? lane : lane - R;
+            double v0 = 0.0, v1 = 0.0;
 #pragma unroll
-            for (int i = 0; i < R; ++i) sh.Pb[i * R + j] = sh.P[i * R + j];
+            for (int k2 = 0; k2 < R; k2 += 2) {
+                v0 = fma(lane < R ? sh.V[j * R + k2] : sh.V[k2 * R + j], sh.xb[k2], v0);
+                if (k2 + 1 < R) v1 = fma(lane < R ? sh.V[j * R + k2 + 1] : sh.V[(k2 + 1) * R + j], sh.xb[k2 + 1], v1);
+            }
+            v = v0 + v1;
+            if (lane < R) sh.vx[j] = v; else sh.vxt[j] = v;
+        }
+        double av = lane < R ? sh.xb[lane] * v : 0.0;
+        av = warp_allsum(av);                                                 // rPSMF.py:93
+        if (lane == 0) {
+            sh.a = av;
+            sh.w1 = 1.0 / (sh.rho + av);
+            sh.w0 = 1.0 / av;
+        }
+    }
+    for (int idx = tid; idx < R * R; idx += nthr) {
+        const int i = idx / R, j = idx % R;
+        double pb;
+        if (simp) {                                                           // synthetic_psmf.py:83-84
+            pb = sh.P[idx];
         } else if (p.dynamics == DYN_EXTERNAL) {                              // psmf.py:115 with a dense F
             const double* F = p.F_ext + (int64_t)series * R * R;
-            double tmp[R];
-#pragma unroll
+            double acc = 0.0;
             for (int k2 = 0; k2 < R; ++k2) {
-                double s = 0.0;
-                for (int l = 0; l < R; ++l) s = fma(sh.P[k2 * R + l], F[j * R + l], s);
-                tmp[k2] = s;
+                double t2 = 0.0;
+                for (int l = 0; l < R; ++l) t2 = fma(sh.P[k2 * R + l], F[j * R + l], t2);
+                acc = fma(F[i * R + k2], t2, acc);
             }
-            for (int i = 0; i < R; ++i) {
-                double s = 0.0;
-#pragma unroll
-                for (int k2 = 0; k2 < R; ++k2) s = fma(F[i * R + k2], tmp[k2], s);
-                sh.Pb[i * R + j] = s + sh.Q[i * R + j];
-            }
+            pb = acc + sh.Q[idx];
         } else {                                                              // rPSMF.py:87 / psmf.py:115
-#pragma unroll
-            for (int i = 0; i < R; ++i) sh.Pb[i * R + j] = sh.fd[i] * sh.P[i * R + j] * sh.fd[j] + sh.Q[i * R + j];
+            pb = sh.fd[i] * sh.P[idx] * sh.fd[j] + sh.Q[idx];
         }
-        double v1 = 0.0, v2 = 0.0;
-#pragma unroll
-        for (int k2 = 0; k2 < R; ++k2) {
-            v1 = fma(sh.V[j * R + k2], sh.xb[k2], v1);
-            v2 = fma(sh.V[k2 * R + j], sh.xb[k2], v2);
-        }
-        sh.vx[j] = v1;
-        sh.vxt[j] = v2;
-        av = sh.xb[j] * v1;
+        sh.Pb[idx] = pb;
     }
-    av = warp_allsum(av);                                                     // rPSMF.py:93
-    if (lane == 0) sh.a = av;
-    __syncwarp();
+    sync_n(nthr);
 }
 
-// Gauss-Jordan with partial pivoting on the R x (2R+1) augmented matrix [I + Pbar G | Pbar | Pbar b] (warp 0).
+// Gauss-Jordan with partial pivoting on the R x (2R+1) augmented matrix [I + Pbar G | Pbar | Pbar b], one
+// element per thread and one barrier per elimination step.  Rows are not swapped: step k eliminates with
+// the unused row of largest |a_ik| (every thread finds it redundantly -> no broadcast barrier) and
+// perm[k] remembers it, so the solution row of unknown k is aug[R & 1][perm[k]].
 template <int R>
-__device__ void gauss_jordan(double (*aug)[2 * R + 2], int lane) {
+__device__ void gauss_jordan_cta(Smem<R>& sh, int tid, int nthr) {
     constexpr int NC = 2 * R + 1;
+    unsigned used = 0;
     for (int k = 0; k < R; ++k) {
-        double v = (lane >= k && lane < R) ? fabs(aug[lane][k]) : -1.0;
-        int pi = lane;
+        const int cur = k & 1, nxt = cur ^ 1;
+        double v[R];
+        int ix[R];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(FULL, v, o);
-            const int oi = __shfl_xor_sync(FULL, pi, o);
-            if (ov > v || (ov == v && oi < pi)) {
-                v = ov;
-                pi = oi;
+        for (int i = 0; i < R; ++i) {
+            v[i] = ((used >> i) & 1u) ? -1.0 : fabs(sh.aug[cur][i][k]);
+            ix[i] = i;
+        }
+#pragma unroll
+        for (int st = 1; st < R; st <<= 1) {
+#pragma unroll
+            for (int i = 0; i + st < R; i += 2 * st) {
+                if (v[i + st] > v[i]) {                 // strict: ties keep the lower row index
+                    v[i] = v[i + st];
+                    ix[i] = ix[i + st];
+                }
             }
         }
-        const double inv = 1.0 / aug[pi][k];
-        __syncwarp();
-        for (int c = lane; c < NC; c += 32) {
-            const double tk = aug[k][c], tp = aug[pi][c];
-            aug[pi][c] = tk;
-            aug[k][c] = tp * inv;
+        const int pi = ix[0];
+        const double inv = 1.0 / sh.aug[cur][pi][k];
+        used |= 1u << pi;
+        if (tid == 0) sh.perm[k] = pi;
+        for (int idx = tid; idx < R * NC; idx += nthr) {
+            const int i = idx / NC, c = idx - i * NC;
+            const double rpc = sh.aug[cur][pi][c] * inv;
+            const double aic = sh.aug[cur][i][c];
+            const double aik = sh.aug[cur][i][k];
+            sh.aug[nxt][i][c] = (i == pi) ? rpc : fma(-aik, rpc, aic);
         }
-        __syncwarp();
-        double f[R];
-#pragma unroll
-        for (int i = 0; i < R; ++i) f[i] = aug[i][k];
-        __syncwarp();
-        for (int c = lane; c < NC; c += 32) {
-            const double rk = aug[k][c];
-#pragma unroll
-            for (int i = 0; i < R; ++i)
-                if (i != k) aug[i][c] = fma(-f[i], rk, aug[i][c]);
-        }
-        __syncwarp();
+        sync_n(nthr);
     }
 }
 
-// ---- r x r part of the step (rPSMF.py:102-115,133-135), identical on every CTA ---------------------
+// ---- r x r part of the step (rPSMF.py:102-115,133-135), identical on every CTA; all `nthr` threads ----
 template <int R>
 __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, int warp, int series, int64_t t,
                              bool writer, int nthr) {
     constexpr int NGm = ngram(R);
+    constexpr int FIN = R & 1;                      // buffer holding the result of the elimination
     const bool simp = (p.flags & F_SIMPLIFIED) != 0;
     const bool robust = (p.flags & F_ROBUST) != 0;
     const double* tot = sh.tot;
@@ -324,19 +347,21 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
                 const int lo = k < j ? k : j, hi = k < j ? j : k;
                 acc = fma(sh.Pb[i * R + k], tot[gram_off(R, lo) + hi - lo], acc);
             }
-            sh.aug[i][j] = acc;
-            sh.aug[i][R + j] = sh.Pb[i * R + j];
+            sh.aug[0][i][j] = acc;
+            sh.aug[0][i][R + j] = sh.Pb[i * R + j];
         }
-        if (tid < R) {                                   // right-hand side Pbar b: the solve then yields K b
+        if (tid >= nthr - R) {                           // right-hand side Pbar b: the solve then yields K b
+            const int i = tid - (nthr - R);
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < R; ++k) acc = fma(sh.Pb[tid * R + k], tot[NGm + k], acc);
-            sh.aug[tid][2 * R] = acc;
+            for (int k = 0; k < R; ++k) acc = fma(sh.Pb[i * R + k], tot[NGm + k], acc);
+            sh.aug[0][i][2 * R] = acc;
         }
+        sync_n(nthr);
+        gauss_jordan_cta<R>(sh, tid, nthr);              // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
     }
-    sync_n(nthr);
+    stamp(p, t, 7);
     if (warp == 0) {
-        if (!simp) gauss_jordan<R>(sh.aug, lane);     // aug[:, R:2R] = K, aug[:, 2R] = K b
         const double a = sh.a, rho = sh.rho, lam = sh.lam;
         const double s = tot[NGm + R], q1 = tot[NGm + R + 1], q0 = tot[NGm + R + 2], nobs = tot[NGm + R + 3];
         const double dg = (double)p.d_global;
@@ -345,14 +370,20 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
             if (simp) {
                 xn = sh.xb[lane];                                              // synthetic_psmf.py:93-94
             } else {
-                const double kb = sh.aug[lane][2 * R];
+                const double kb = sh.aug[FIN][sh.perm[lane]][2 * R];
                 xn = sh.xb[lane] + kb;                                         // rPSMF.py:104
                 bkb = tot[NGm + lane] * kb;
+                double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
+                for (int i = 0; i < R; i += 2) {
                     const int lo = i < lane ? i : lane, hi = i < lane ? lane : i;
-                    trpg = fma(sh.Pb[i * R + lane], tot[gram_off(R, lo) + hi - lo], trpg);
+                    t0 = fma(sh.Pb[i * R + lane], tot[gram_off(R, lo) + hi - lo], t0);
+                    if (i + 1 < R) {
+                        const int lo1 = i + 1 < lane ? i + 1 : lane, hi1 = i + 1 < lane ? lane : i + 1;
+                        t1 = fma(sh.Pb[(i + 1) * R + lane], tot[gram_off(R, lo1) + hi1 - lo1], t1);
+                    }
                 }
+                trpg = t0 + t1;
             }
         }
         bkb = warp_allsum(bkb);
@@ -368,24 +399,13 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         const double omega = robust ? (lam + sSe) / (lam + dg) : 1.0;          // rPSMF.py:105
         const double N = a + eta;                                              // rPSMF.py:109
         const double phi = robust ? (lam + q1 / (a + eta) + (q0 != 0.0 ? q0 / eta : 0.0)) / (lam + dg) : 1.0;
-        const double aphi = p.alpha * phi, bom = p.beta * omega;
         if (lane < R) {
-            const int j = lane;
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const double pn = simp ? sh.Pb[i * R + j] : bom * sh.aug[i][R + j];          // rPSMF.py:106
-                const double vn = aphi * (sh.V[i * R + j] - sh.vx[i] * sh.vxt[j] / N);       // rPSMF.py:115
-                sh.P[i * R + j] = pn;
-                sh.V[i * R + j] = vn;
-                if (!simp) sh.Q[i * R + j] = omega * sh.Q[i * R + j];                        // rPSMF.py:133
-            }
-            sh.x[j] = xn;
-            sh.g[j] = (((p.flags & F_CUPDATE_VT) != 0) ? sh.vx[j] : sh.vxt[j]) / N;          // rPSMF.py:111 / PSMF.py:80
-            if (writer && p.X_out != nullptr) p.X_out[((int64_t)series * p.n_steps + t) * R + j] = xn;
+            sh.x[lane] = xn;
+            if (writer && p.X_out != nullptr) p.X_out[((int64_t)series * p.n_steps + t) * R + lane] = xn;
         }
         if (lane == 0) {
-            sh.rho = omega * rho;                                              // rPSMF.py:134
-            sh.lam = (robust && (p.flags & F_FIXED_LAMBDA) == 0) ? lam + dg : lam;   // rPSMF.py:135
+            sh.sc[0] = omega; sh.sc[1] = eta; sh.sc[2] = N; sh.sc[3] = phi; sh.sc[4] = sSe;
+            sh.sc[5] = p.alpha * phi; sh.sc[6] = p.beta * omega;
             if (writer) {
                 if (p.scal_out != nullptr) {
                     double* so = p.scal_out + ((int64_t)series * p.n_steps + t) * NSCAL;
@@ -395,8 +415,88 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
                     atomicCAS((unsigned long long*)p.status, ~0ULL, (unsigned long long)t);
             }
         }
-        __syncwarp();
-        if (t + 1 < p.n_steps) predict<R>(p, sh, lane, p.k0 + t + 1, series);
+    }
+    sync_n(nthr);
+    {
+        const double omega = sh.sc[0], N = sh.sc[2], aphi = sh.sc[5], bom = sh.sc[6];
+        for (int idx = tid; idx < R * R; idx += nthr) {
+            const int i = idx / R, j = idx % R;
+            const double pn = simp ? sh.Pb[idx] : bom * sh.aug[FIN][sh.perm[i]][R + j];      // rPSMF.py:106
+            const double vn = aphi * (sh.V[idx] - sh.vx[i] * sh.vxt[j] / N);                 // rPSMF.py:115
+            sh.P[idx] = pn;
+            sh.V[idx] = vn;
+            if (!simp) sh.Q[idx] = omega * sh.Q[idx];                                        // rPSMF.py:133
+        }
+        if (tid >= nthr - R) {
+            const int j = tid - (nthr - R);
+            sh.g[j] = (((p.flags & F_CUPDATE_VT) != 0) ? sh.vx[j] : sh.vxt[j]) / N;          // rPSMF.py:111 / PSMF.py:80
+        }
+        if (tid == nthr - 32) {
+            const double lam = sh.lam;
+            sh.rho = omega * sh.rho;                                                         // rPSMF.py:134
+            sh.lam = (robust && (p.flags & F_FIXED_LAMBDA) == 0) ? lam + (double)p.d_global : lam;   // rPSMF.py:135
+        }
+    }
+    sync_n(nthr);
+    if (t + 1 < p.n_steps) predict_cta<R>(p, sh, tid, p.k0 + t + 1, series, nthr);
+}
+
+// ---- cross-CTA reduction of the statistics, deterministic (fixed summation order) ---------------------
+//   cps <= 16 : every CTA reads all partials after one grid barrier
+//   cps  > 16 : reduce-scatter / all-gather through L2: CTA c sums entries {c, c + cps, ..} over all CTAs
+//               (coalesced reads of a transposed partial array), a second barrier publishes the totals.
+// sh.part -> sh.tot; ends with a barrier over the `nthr` threads.
+template <int R>
+__device__ __forceinline__ void grid_reduce(const KParams& p, Smem<R>& sh, int tid, int lane, int warp, int64_t t,
+                                            int series, int part, int nthr) {
+    constexpr int NSP = nstat_pad(R), NST = nstat(R);
+    if (p.cps == 1) {
+        if (tid < NST) sh.tot[tid] = sh.part[tid];
+        sync_n(nthr);
+        return;
+    }
+    const int parity = (int)(t & 1);
+    const int cps = p.cps;
+    if (cps <= 16) {
+        double* mine = p.partials + ((size_t)parity * cps + part) * NSP;
+        if (tid < NST) mine[tid] = sh.part[tid];
+        stamp(p, t, 3);
+        grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), nthr);
+        stamp(p, t, 4);
+        const double* basep = p.partials + (size_t)parity * cps * NSP;
+        if (tid < NST) {
+            double v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = c < cps ? __ldcg(basep + (size_t)c * NSP + tid) : 0.0;
+            sh.tot[tid] = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) +
+                          (((v[8] + v[9]) + (v[10] + v[11])) + ((v[12] + v[13]) + (v[14] + v[15])));
+        }
+    } else {
+        const int pstr = (cps + 7) & ~7;
+        double* pT = p.partials + (size_t)parity * NSP * (pstr + 1);
+        double* totals = pT + (size_t)NSP * pstr;
+        if (tid < NST) pT[(size_t)tid * pstr + part] = sh.part[tid];
+        stamp(p, t, 3);
+        grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 1), nthr);
+        const int nw = nthr >> 5;
+        for (int e = part + warp * cps; e < NST; e += nw * cps) {
+            const double* src = pT + (size_t)e * pstr;
+            double s = 0.0;
+            for (int c0 = 0; c0 < cps; c0 += 256) {
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + lane + 32 * j;
+                    v[j] = c < cps ? __ldcg(src + c) : 0.0;
+                }
+                s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            }
+            s = warp_allsum(s);
+            if (lane == 0) totals[e] = s;
+        }
+        grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 2), nthr);
+        stamp(p, t, 4);
+        if (tid < NST) sh.tot[tid] = __ldcg(totals + tid);
     }
     sync_n(nthr);
 }
@@ -437,15 +537,17 @@ __global__ void __launch_bounds__(nsplit_for(R) * ngroups_for(R) * 32, 1) psmf_f
     }
     for (int i = tid; i < (te - tb) * TILE; i += blockDim.x) ebuf[i] = 0.0;
     __syncthreads();
-    if (warp == 0) predict<R>(p, sh, lane, p.k0, series);
-    __syncthreads();
+    predict_cta<R>(p, sh, tid, p.k0, series, blockDim.x);
 
     for (int64_t t = 0; t < p.n_steps; ++t) {
         const T* Yt = reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst + t * p.ldy;
         const uint8_t* Mt = p.M ? p.M + (int64_t)series * p.msst + t * p.ldm : nullptr;
         T* Yrec_t = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + t * p.ldrec : nullptr;
+        stamp(p, t, 0);
         dispatch_pass<R, T, 0>(role, p, sh, ebuf, Cs, Yt, Mt, Yrec_t, tb, te, group, lane);
+        stamp(p, t, 1);
         __syncthreads();
+        stamp(p, t, 2);
         // CTA partial: fixed order over the row groups
         if (tid < NST) {
             double s = 0.0;
@@ -453,30 +555,10 @@ __global__ void __launch_bounds__(nsplit_for(R) * ngroups_for(R) * 32, 1) psmf_f
             for (int g = 0; g < NG; ++g) s += sh.red[g * NSP + tid];
             sh.part[tid] = s;
         }
-        if (p.cps > 1) {
-            const int parity = (int)(t & 1);
-            double* mine = p.partials + ((size_t)parity * gridDim.x + blockIdx.x) * NSP;
-            if (tid < NST) mine[tid] = sh.part[tid];
-            grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), blockDim.x);
-            const double* basep = p.partials + ((size_t)parity * gridDim.x + (size_t)series * p.cps) * NSP;
-            if (tid < NST) {
-                // fixed summation order: 4 interleaved chains over the CTAs, combined as (s0+s1)+(s2+s3)
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int c = 0;
-                for (; c + 3 < p.cps; c += 4) {
-                    s0 += __ldcg(basep + (size_t)(c + 0) * NSP + tid);
-                    s1 += __ldcg(basep + (size_t)(c + 1) * NSP + tid);
-                    s2 += __ldcg(basep + (size_t)(c + 2) * NSP + tid);
-                    s3 += __ldcg(basep + (size_t)(c + 3) * NSP + tid);
-                }
-                for (; c < p.cps; ++c) s0 += __ldcg(basep + (size_t)c * NSP + tid);
-                sh.tot[tid] = (s0 + s1) + (s2 + s3);
-            }
-        } else {
-            if (tid < NST) sh.tot[tid] = sh.part[tid];
-        }
-        __syncthreads();
+        grid_reduce<R>(p, sh, tid, lane, warp, t, series, part, blockDim.x);
+        stamp(p, t, 5);
         small_update<R>(p, sh, tid, lane, warp, series, t, writer, blockDim.x);
+        stamp(p, t, 6);
     }
 
     dispatch_flush<R, T, 0>(role, sh, ebuf, Cs, tb, te, group, lane);

@@ -119,7 +119,7 @@ __device__ __forceinline__ void s_role_pass(const KParams& p, Smem<R>& sh, doubl
     constexpr int JB = s_split_begin(R, Q), JE = s_split_begin(R, Q + 1);
     constexpr int NGR = gram_off(R, JE) - gram_off(R, JB);
     constexpr int NACC = FLUSH ? 1 : NGR + (Q == 0 ? R + 4 : 0);
-    const double a = sh.a, rho = sh.rho;
+    const double w1 = sh.w1, w0 = sh.w0;
     const int nchunks = (nt + TS - 1) / TS;
     const bool streaming = nchunks > nslot;
     double acc[NACC];
@@ -157,8 +157,8 @@ __device__ __forceinline__ void s_role_pass(const KParams& p, Smem<R>& sh, doubl
             for (int j = JB; j < R; ++j) c[j] = fma(ep, sh.g[j], c[j]);      // rPSMF.py:111 (previous step)
 #pragma unroll
             for (int j = JB; j < JE; ++j) ct[j * TILE] = (T)c[j];
-            const double w = 1.0 / ((mi ? rho : 0.0) + a);                    // rPSMF.py:92,98,32
-            const double mw = mi ? w : 0.0;
+            const double w = mi ? w1 : w0;                                    // rPSMF.py:92,98,32
+            const double mw = mi ? w1 : 0.0;
 #pragma unroll
             for (int j = JB; j < JE; ++j) {
                 const double cw = c[j] * mw;
@@ -169,9 +169,10 @@ __device__ __forceinline__ void s_role_pass(const KParams& p, Smem<R>& sh, doubl
                 }
             }
             if (Q == 0) {
-                double yh = 0.0;
+                double yh4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                for (int j = 0; j < R; ++j) yh = fma(c[j], sh.xb[j], yh);     // rPSMF.py:89
+                for (int j = 0; j < R; ++j) yh4[j & 3] = fma(c[j], sh.xb[j], yh4[j & 3]);   // rPSMF.py:89
+                const double yh = (yh4[0] + yh4[1]) + (yh4[2] + yh4[3]);
                 const double e = yi - (mi ? yh : 0.0);                        // rPSMF.py:101
                 ebuf[rl] = e;
                 if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
@@ -352,42 +353,25 @@ __global__ void __launch_bounds__(s_threads(R), 1) psmf_stream_kernel(const KPar
     const int group = warp / NS;
     const int role = ((warp % NS) + group) % NS;
     const bool masked = p.M != nullptr;
-    if (warp == 0) predict<R>(p, sh, lane, p.k0, series);
-    sync_n(NCT);
+    predict_cta<R>(p, sh, tid, p.k0, series, NCT);
 
     for (int64_t t = 0; t < p.n_steps; ++t) {
         T* Yrec_t = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + t * p.ldrec : nullptr;
+        stamp(p, t, 0);
         s_dispatch<R, T, false, 0>(role, p, sh, ebuf, slots, full, done, Yrec_t, masked, tb, nt, nslot, t, group, lane);
+        stamp(p, t, 1);
         sync_n(NCT);
+        stamp(p, t, 2);
         if (tid < NST) {
             double s = 0.0;
 #pragma unroll
             for (int g = 0; g < NG; ++g) s += sh.red[g * NSP + tid];
             sh.part[tid] = s;
         }
-        if (p.cps > 1) {
-            const int parity = (int)(t & 1);
-            double* mine = p.partials + ((size_t)parity * gridDim.x + blockIdx.x) * NSP;
-            if (tid < NST) mine[tid] = sh.part[tid];
-            grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), NCT);
-            const double* basep = p.partials + ((size_t)parity * gridDim.x + (size_t)series * p.cps) * NSP;
-            if (tid < NST) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int c = 0;
-                for (; c + 3 < p.cps; c += 4) {
-                    s0 += __ldcg(basep + (size_t)(c + 0) * NSP + tid);
-                    s1 += __ldcg(basep + (size_t)(c + 1) * NSP + tid);
-                    s2 += __ldcg(basep + (size_t)(c + 2) * NSP + tid);
-                    s3 += __ldcg(basep + (size_t)(c + 3) * NSP + tid);
-                }
-                for (; c < p.cps; ++c) s0 += __ldcg(basep + (size_t)c * NSP + tid);
-                sh.tot[tid] = (s0 + s1) + (s2 + s3);
-            }
-        } else {
-            if (tid < NST) sh.tot[tid] = sh.part[tid];
-        }
-        sync_n(NCT);
+        grid_reduce<R>(p, sh, tid, lane, warp, t, series, part, NCT);
+        stamp(p, t, 5);
         small_update<R>(p, sh, tid, lane, warp, series, t, writer, NCT);
+        stamp(p, t, 6);
     }
 
     // flush pass: pending rank-1 update of the last step

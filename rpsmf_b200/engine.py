@@ -230,6 +230,12 @@ class FilterEngine:
         self._ck(self._L.psmf_status(self._h, C.byref(bad)))
         return int(bad.value)
 
+    def set_trace(self, steps):
+        """Debug: record phase time stamps (ns, globaltimer) of CTA 0 for the first `steps` steps of each run."""
+        self._trace = torch.zeros((steps, 8), dtype=torch.int64, device=self.device) if steps else None
+        self._ck(self._L.psmf_set_trace(self._h, C.c_void_p(self._trace.data_ptr()) if steps else None, int(steps)))
+        return self._trace
+
     def launch_info(self):
         a, b, c, dd = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         self._ck(self._L.psmf_launch_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(dd)))
