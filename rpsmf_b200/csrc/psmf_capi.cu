@@ -40,7 +40,7 @@ __global__ void pack_C(const T* __restrict__ src, T* __restrict__ dst, int64_t d
         const int j = (int)((idx / TILE) % R);
         const int64_t tile = (idx / (TILE * (int64_t)R)) % ntiles;
         const int64_t s = idx / (TILE * (int64_t)R * ntiles);
-        const int64_t row = tile * TILE + l;
+        const int64_t row = tile * TILE + (l ^ ((j & 7) << 2));        // inverse of tile_pos (XOR swizzle)
         dst[idx] = row < d ? src[(s * d + row) * R + j] : (T)0;
     }
 }
@@ -51,7 +51,7 @@ __global__ void unpack_C(const T* __restrict__ src, T* __restrict__ dst, int64_t
         const int j = (int)((idx / TILE) % R);
         const int64_t tile = (idx / (TILE * (int64_t)R)) % ntiles;
         const int64_t s = idx / (TILE * (int64_t)R * ntiles);
-        const int64_t row = tile * TILE + l;
+        const int64_t row = tile * TILE + (l ^ ((j & 7) << 2));
         if (row < d) dst[(s * d + row) * R + j] = src[idx];
     }
 }
@@ -148,22 +148,22 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     e->num_sms = sms;
 
-    const int NG = ngroups_for(e->R);
-    // CTAs per series
+    // ---- direct-load kernel: V1_WARPS warps per CTA, one staging tile per warp + the residual buffer ----
     int cps;
     if (e->S > 1) {
         cps = 1;
     } else if (cfg->ctas > 0) {
         cps = cfg->ctas;
     } else {
-        int64_t want = e->ntiles / (2 * NG);
+        int64_t want = e->ntiles / (2 * V1_WARPS);
         cps = (int)(want < 1 ? 1 : (want > sms ? sms : want));
     }
     if ((int64_t)cps > e->ntiles) cps = (int)e->ntiles;
+    const size_t stage_bytes = (size_t)V1_WARPS * e->R * TILE * sizeof(double);
     LaunchShape shp;
     for (;;) {
         const int64_t tiles_per = (e->ntiles + cps - 1) / cps + 1;
-        e->dyn_smem = (size_t)tiles_per * TILE * sizeof(double);
+        e->dyn_smem = stage_bytes + (size_t)tiles_per * TILE * sizeof(double);
         ce = SHAPE[e->R](cfg->dtype, e->dyn_smem, &shp);
         if (ce == cudaSuccess && shp.max_ctas_per_sm >= 1) break;
         cudaGetLastError();
@@ -180,17 +180,16 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     e->threads = shp.threads;
     e->cooperative = cps > 1;
 
-    // ---- TMA-staged kernel: slots of (2 * groups) tiles + y/m slices, residual buffer behind them ----
+    // ---- TMA-staged kernel: slots of V2_TS tiles + y/m slices, residual buffer behind them ----
     if (cfg->kernel != 1 && e->d % 16 == 0) {
-        const int NG2 = e->R <= 6 ? 8 : (e->R <= 10 ? 6 : 3);
-        const int TS = 2 * NG2;
+        const int TS = V2_TS;
         auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
         const size_t slot = r128((size_t)TS * e->R * TILE * e->esize) + r128((size_t)TS * TILE * e->esize) + r128((size_t)TS * TILE);
         int cps2;
         if (e->S > 1) cps2 = 1;
         else if (cfg->ctas > 0) cps2 = cfg->ctas;
         else {
-            int64_t want = e->ntiles / TS;
+            int64_t want = e->ntiles / (V2_CWARPS + 1);                 // about one tile per consumer warp and step
             cps2 = (int)(want < 1 ? 1 : (want > sms ? sms : want));
         }
         if ((int64_t)cps2 > e->ntiles) cps2 = (int)e->ntiles;
@@ -348,9 +347,8 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     bool aligned = h->cps2 > 0 && ((uintptr_t)io->Y % 16 == 0) && ((size_t)io->ldy * es % 16 == 0) &&
                    ((size_t)io->y_series_stride * es % 16 == 0);
     if (io->M) aligned = aligned && ((uintptr_t)io->M % 16 == 0) && (io->ldm % 16 == 0) && (io->m_series_stride % 16 == 0);
-    const int NG2 = h->R <= 6 ? 8 : (h->R <= 10 ? 6 : 3);
     bool use2 = aligned && h->cfg.dynamics != PSMF_DYN_EXTERNAL &&
-                (h->cfg.kernel == 2 || (h->cfg.kernel == 0 && h->ntiles >= 8 * NG2));
+                (h->cfg.kernel == 2 || (h->cfg.kernel == 0 && h->ntiles >= 2 * (V2_CWARPS + 1)));
     if (h->cfg.kernel == 2 && !use2)
         return fail(h, PSMF_E_INVALID, "kernel=2 requested but Y/M are not 16-byte aligned (or dynamics is external)");
     if (use2) {

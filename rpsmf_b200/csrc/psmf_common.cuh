@@ -2,8 +2,8 @@
 //
 // Data layout in HBM
 //   C      tiled structure-of-arrays: rows are grouped in tiles of 32; inside a tile the layout is
-//          [r][32] (column-major), i.e. element (i, j) lives at
-//              tile(i) * (R*32) + j*32 + (i & 31).
+//          [r][32] (column-major) with an XOR swizzle of the row index (tile_pos below), i.e. element
+//          (i, j) lives at   tile(i) * (R*32) + j*32 + ((i & 31) ^ ((j & 7) << 2)).
 //          A warp that maps lane -> row reads column j of a tile as one 256-byte coalesced request,
 //          and a tile is one contiguous R*256-byte block (bulk-copy friendly).
 //   Y, M   time-major (T, ld): the d values of one time step are contiguous.
@@ -23,38 +23,24 @@ constexpr int MAX_PEERS = 8;
 constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16;
 constexpr int DYN_IDENTITY = 0, DYN_COS = 1, DYN_EXTERNAL = 3;
 
-// ---- compile-time work split ---------------------------------------------------------------------
-// The upper triangle of the r x r Gram matrix (r(r+1)/2 fp64 accumulators) does not fit one thread's
-// registers at r = 16, so a 32-row tile is processed by NSPLIT warps ("roles"); role q owns Gram rows
-// j in [split_begin(q), split_begin(q+1)) and therefore needs columns j >= split_begin(q) of C.
-// Role 0 additionally owns y_hat, e, b, s, q1, q0, n_obs.
-__host__ __device__ constexpr int nsplit_for(int R) { return R <= 6 ? 1 : (R <= 10 ? 2 : 4); }
-__host__ __device__ constexpr int ngroups_for(int R) { return R <= 6 ? 8 : (R <= 10 ? 6 : 3); }
+// ---- tile layout and statistics vector ------------------------------------------------------------
+// Inside a 32-row tile, element (row i, column j) lives at  j*32 + (i ^ ((j & 7) << 2)).
+// The XOR swizzle keeps BOTH access patterns of the kernels at the shared-memory bank-conflict floor:
+//   * lane = row (rank-1 update, y_hat, e):   a column is a permuted, contiguous 256-byte segment
+//   * DMMA fragments of the Gram (lane -> (column lane/4, row 4s + lane%4)): 32 distinct 8-byte banks x2
+__host__ __device__ constexpr int tile_pos(int j, int i) { return j * 32 + (i ^ ((j & 7) << 2)); }
+
+constexpr int V1_WARPS = 8;     // direct-load kernel: warps per CTA (one tile per warp at a time)
+constexpr int V2_CWARPS = 15;   // TMA-staged kernel: consumer warps (+1 producer warp)
+constexpr int V2_TS = 4;        // TMA-staged kernel: tiles per shared-memory chunk slot
+constexpr int MAXW = 15;        // max consumer warps of any kernel (sizes the per-warp partial buffer)
+
 __host__ __device__ constexpr int ngram(int R) { return R * (R + 1) / 2; }
+// statistics: packed upper triangle of G, then b (R), s, q1, q0, n_obs
 __host__ __device__ constexpr int nstat(int R) { return ngram(R) + R + 4; }
 __host__ __device__ constexpr int nstat_pad(int R) { return (nstat(R) + 7) / 8 * 8; }
 // packed index of Gram entry (j, j) in row-major upper-triangular order
 __host__ __device__ constexpr int gram_off(int R, int j) { return j * R - j * (j - 1) / 2; }
-
-__host__ __device__ constexpr int split_begin(int R, int NS, int q) {
-    if (q <= 0) return 0;
-    if (q >= NS) return R;
-    const int total = ngram(R) + 3 * R;     // role 0 carries ~3R extra FMAs per row (update, y_hat, b)
-    int acc = 3 * R;
-    int j = 0;
-    for (int role = 0; role < q; ++role) {
-        const int target = (total * (role + 1) + NS - 1) / NS;
-        const int start = j;
-        while (j < R) {
-            const int later = NS - 1 - role;
-            if (R - j <= later) break;                 // keep at least one Gram row for every later role
-            if (j > start && acc >= target) break;
-            acc += R - j;
-            ++j;
-        }
-    }
-    return j;
-}
 
 // small-state layout (doubles per series)
 __host__ __device__ constexpr int st_x(int R) { return 0; }

@@ -1,12 +1,18 @@
-// Persistent PSMF / rPSMF filter kernel (sm_100a): one launch runs n_steps filter steps.
+// PSMF / rPSMF filter on sm_100a: shared device code + the direct-load persistent kernel.
 //
 // Per step (reference ExperimentImpute/rPSMF.py:81-135, PSMF.py:60-84,
 // pypsmf/psmf/psmf.py:90-165, rpsmf.py:116-171):
 //
-//   row pass   (all warps)  c_i += e_i(t-1) g(t-1)            rank-1 update of the PREVIOUS step, fused in
-//                            yhat_i = c_i . xbar ; e_i = y_i - m_i yhat_i ; w_i = 1/(m_i rho + a)
-//                            G += m w c c' ; b += m w e c ; s += w e^2 ; q1, q0, n_obs
-//   reduce     warp butterfly -> CTA (fixed order) -> grid (fixed CTA order, one grid barrier)
+//   row pass   one warp per 32-row tile, all warps independent
+//              phase 1 (lane = row)   c_i += e_i(t-1) g(t-1)        rank-1 update of the PREVIOUS step, fused in
+//                                     yhat_i = c_i . xbar ; e_i = y_i - m_i yhat_i ; w_i in {1/(rho+a), 1/a}
+//                                     b += m w e c ; s += w e^2 ; q1, q0, n_obs
+//              phase 2 (fragments)    G += sum_i m_i c_i c_i'  as fp64 DMMA.8x8x4 on the updated tile in
+//                                     shared memory: the k-dimension of the MMA is the row index, so the
+//                                     r(r+1)/2 Gram entries need 6 accumulator registers per thread instead
+//                                     of 136 (measured on B200: DMMA runs at exactly the DFMA pipe rate, so
+//                                     this is a register / latency optimisation, not a FLOP one)
+//   reduce     warp -> CTA (fixed order) -> grid (fixed order; one or two grid barriers)
 //   small      K = (I + Pbar G)^-1 Pbar (Gauss-Jordan, partial pivoting, fp64), x, omega, P, eta, N, phi,
 //              V, Q, rho, lambda, g = V xbar / N, then the predict half of the next step
 //
@@ -22,7 +28,6 @@ constexpr unsigned FULL = 0xffffffffu;
 
 template <int R>
 struct Smem {
-    static constexpr int NG = ngroups_for(R);
     static constexpr int NSP = nstat_pad(R);
     double x[R];        // x_{t-1}, then x_t
     double xb[R];       // x_bar = f(x_{t-1})
@@ -35,7 +40,7 @@ struct Smem {
     double aug[2][R][2 * R + 2];   // double-buffered augmented matrix of the r x r solve
     double tot[NSP];
     double part[NSP];
-    double red[NG * NSP];          // per row-group partial statistics
+    double red[MAXW * NSP];        // per-warp partial statistics
     double a, rho, lam;
     double w1, w0;                 // 1/(rho + a), 1/a : the only two values of w_i (rPSMF.py:92,98,32)
     double sc[8];                  // omega, eta, N, phi, sSe, alpha*phi, beta*omega
@@ -84,6 +89,15 @@ __device__ __forceinline__ double warp_allsum(double v) {
     return v;   // bit-identical on every lane (a+b == b+a at every stage)
 }
 
+// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (the pivots of the solve are O(1) or larger)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 // Transposing butterfly: reduces N per-lane accumulators over the 32 lanes with ~N shuffles instead of
 // 5N.  On return lane l holds the full sums of entries [base, base + bfly_final(N)).
 __host__ __device__ constexpr int bfly_final(int n) {
@@ -108,119 +122,89 @@ __device__ __forceinline__ void bfly(double (&v)[NA], int lane, int& base, int& 
     if constexpr (O > 1) bfly<H, O / 2, NA>(v, lane, base, lim);
 }
 
-// ---- row pass of one role over the CTA's tiles ----------------------------------------------------
-template <int R, int Q, typename T>
-__device__ __forceinline__ void role_pass(const KParams& p, Smem<R>& sh, double* __restrict__ ebuf, T* __restrict__ Cs,
-                                          const T* __restrict__ Yt, const uint8_t* __restrict__ Mt,
-                                          T* __restrict__ Yrec_t, int tb, int te, int group, int lane) {
-    constexpr int NS = nsplit_for(R), NG = ngroups_for(R), NSP = nstat_pad(R);
-    constexpr int JB = split_begin(R, NS, Q), JE = split_begin(R, NS, Q + 1);
-    constexpr int NGR = gram_off(R, JE) - gram_off(R, JB);
-    constexpr int NACC = NGR + (Q == 0 ? R + 4 : 0);
-    const double w1 = sh.w1, w0 = sh.w0;
-    double acc[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+// ---- per-warp statistics of one pass -------------------------------------------------------------------
+// D(8x8) += A(8x4) * B(4x8), fp64 (SASS: DMMA.8x8x4).  Fragments: a = A[lane/4][lane%4],
+// b = B[lane%4][lane/4], d[0..1] = D[lane/4][2*(lane%4) + 0..1].
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
 
-    for (int tile = tb + group; tile < te; tile += NG) {
-        const int64_t row = (int64_t)tile * TILE + lane;
-        const int rl = (tile - tb) * TILE + lane;
-        T* ct = Cs + (int64_t)tile * (R * TILE) + lane;
-        double c[R];
+template <int R>
+struct TileAcc {
+    double g00[2], g01[2], g11[2];   // fragments of sum_i m_i c_i c_i' : blocks (0..7,0..7), (0..7,8..15), (8..15,8..15)
+    double v[R + 4];                 // per-lane: b (R), s, q1, q0, n_obs
+    __device__ __forceinline__ void zero() {
+        g00[0] = g00[1] = g01[0] = g01[1] = g11[0] = g11[1] = 0.0;
 #pragma unroll
-        for (int j = JB; j < R; ++j) c[j] = (double)ct[j * TILE];
-        const double ep = ebuf[rl];
-        const bool inb = row < p.d;
-        bool mi = inb;
-        if (Mt != nullptr && inb) mi = Mt[row] != 0;
-        double yi = 0.0;
-        if (Q == 0 && inb) yi = (double)Yt[row];
-        // every role has read what it needs of this tile (C columns, e of the previous step) before any
-        // role overwrites it
-        if (NS > 1) named_bar_sync(1 + group, NS * 32);
-#pragma unroll
-        for (int j = JB; j < R; ++j) c[j] = fma(ep, sh.g[j], c[j]);          // rPSMF.py:111 (previous step)
-#pragma unroll
-        for (int j = JB; j < JE; ++j) ct[j * TILE] = (T)c[j];
-        const double w = mi ? w1 : w0;                                        // rPSMF.py:92,98,32
-        const double mw = mi ? w1 : 0.0;
-#pragma unroll
-        for (int j = JB; j < JE; ++j) {
-            const double cw = c[j] * mw;
-#pragma unroll
-            for (int k = j; k < R; ++k) {
-                const int idx = gram_off(R, j) - gram_off(R, JB) + (k - j);
-                acc[idx] = fma(cw, c[k], acc[idx]);                           // G = CM' Ri CM, rPSMF.py:35
-            }
-        }
-        if (Q == 0) {
-            double yh4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int j = 0; j < R; ++j) yh4[j & 3] = fma(c[j], sh.xb[j], yh4[j & 3]);   // rPSMF.py:89
-            const double yh = (yh4[0] + yh4[1]) + (yh4[2] + yh4[3]);
-            const double e = yi - (mi ? yh : 0.0);                            // rPSMF.py:101
-            ebuf[rl] = e;
-            if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
-            const double ew = e * mw;
-#pragma unroll
-            for (int j = 0; j < R; ++j) acc[NGR + j] = fma(ew, c[j], acc[NGR + j]);
-            const double e2 = e * e;
-            acc[NGR + R + 0] = fma(inb ? w : 0.0, e2, acc[NGR + R + 0]);      // diff' Ri diff
-            acc[NGR + R + 1] += mi ? e2 : 0.0;                                // rPSMF.py:112-114 (observed rows)
-            acc[NGR + R + 2] += mi ? 0.0 : e2;                                //                  (missing rows)
-            acc[NGR + R + 3] += mi ? 1.0 : 0.0;
-        }
+        for (int i = 0; i < R + 4; ++i) v[i] = 0.0;
     }
+};
 
-    int base = 0, lim = NACC;
-    bfly<NACC, 16, NACC>(acc, lane, base, lim);
-    constexpr int NF = bfly_final(NACC);
+// phase 1 for one row (lane = row): c holds the row on entry, the updated row on exit.
+template <int R>
+__device__ __forceinline__ void row_stats(TileAcc<R>& A, const Smem<R>& sh, double (&c)[R], double ep, bool inb, bool mi,
+                                          double yi, double w1, double w0, double& e, double& yh) {
 #pragma unroll
-    for (int i = 0; i < NF; ++i) {
-        const int li = base + i;
-        if (li < lim) {
-            int gi;
-            if (Q == 0)
-                gi = li < NGR ? li : ngram(R) + (li - NGR);
-            else
-                gi = gram_off(R, JB) + li;
-            sh.red[group * NSP + gi] = acc[i];
+    for (int j = 0; j < R; ++j) c[j] = fma(ep, sh.g[j], c[j]);                // rPSMF.py:111 (previous step)
+    double yh4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < R; ++j) yh4[j & 3] = fma(c[j], sh.xb[j], yh4[j & 3]);   // rPSMF.py:89
+    yh = (yh4[0] + yh4[1]) + (yh4[2] + yh4[3]);
+    e = yi - (mi ? yh : 0.0);                                                  // rPSMF.py:101
+    const double w = mi ? w1 : w0;                                             // rPSMF.py:92,98,32
+    const double ew = mi ? e * w1 : 0.0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) A.v[j] = fma(ew, c[j], A.v[j]);               // b = CM' Ri diff
+    const double e2 = e * e;
+    A.v[R + 0] = fma(inb ? w : 0.0, e2, A.v[R + 0]);                           // diff' Ri diff
+    A.v[R + 1] += mi ? e2 : 0.0;                                               // rPSMF.py:112-114 (observed rows)
+    A.v[R + 2] += mi ? 0.0 : e2;                                               //                  (missing rows)
+    A.v[R + 3] += mi ? 1.0 : 0.0;
+}
+
+// phase 2: masked Gram of the updated tile (swizzled [R][32] layout in shared memory).  mbits = ballot of m_i.
+template <int R, typename TS>
+__device__ __forceinline__ void tile_gram(TileAcc<R>& A, const TS* __restrict__ tile, unsigned mbits, int lane) {
+    const int kk = lane & 3, mm = lane >> 2;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const int row = 4 * s + kk;
+        const bool mrow = (mbits >> row) & 1u;
+        const int pos = row ^ (mm << 2);                       // tile_pos(mm, row) - mm*32 == tile_pos(8+mm, row) - (8+mm)*32
+        const double a0 = (mm < R) ? (double)tile[mm * 32 + pos] : 0.0;
+        const double b0 = mrow ? a0 : 0.0;
+        dmma884(A.g00, a0, b0);
+        if constexpr (R > 8) {
+            const double a1 = (8 + mm < R) ? (double)tile[(8 + mm) * 32 + pos] : 0.0;
+            const double b1 = mrow ? a1 : 0.0;
+            dmma884(A.g01, a0, b1);
+            dmma884(A.g11, a1, b1);
         }
     }
 }
 
-// apply the pending rank-1 update of the last step so that C in HBM is the filtered C_T
-template <int R, int Q, typename T>
-__device__ __forceinline__ void role_flush(Smem<R>& sh, const double* __restrict__ ebuf, T* __restrict__ Cs, int tb,
-                                           int te, int group, int lane) {
-    constexpr int NS = nsplit_for(R), NG = ngroups_for(R);
-    constexpr int JB = split_begin(R, NS, Q), JE = split_begin(R, NS, Q + 1);
-    for (int tile = tb + group; tile < te; tile += NG) {
-        const int rl = (tile - tb) * TILE + lane;
-        T* ct = Cs + (int64_t)tile * (R * TILE) + lane;
-        const double ep = ebuf[rl];
+// end of pass: this warp's partial statistics -> red[0 .. nstat(R))   (G = w1 * sum m c c', rPSMF.py:35)
+template <int R>
+__device__ __forceinline__ void acc_writeout(TileAcc<R>& A, double* __restrict__ red, double w1, int lane) {
+    const int kk = lane & 3, mm = lane >> 2;
 #pragma unroll
-        for (int j = JB; j < JE; ++j) ct[j * TILE] = (T)fma(ep, sh.g[j], (double)ct[j * TILE]);
+    for (int x = 0; x < 2; ++x) {
+        const int n = 2 * kk + x;
+        if (mm <= n && n < R) red[gram_off(R, mm) + (n - mm)] = w1 * A.g00[x];
+        if constexpr (R > 8) {
+            if (8 + n < R) red[gram_off(R, mm) + (8 + n - mm)] = w1 * A.g01[x];
+            if (mm <= n && 8 + n < R) red[gram_off(R, 8 + mm) + (n - mm)] = w1 * A.g11[x];
+        }
     }
-}
-
-template <int R, typename T, int Q>
-__device__ __forceinline__ void dispatch_pass(int role, const KParams& p, Smem<R>& sh, double* ebuf, T* Cs, const T* Yt,
-                                              const uint8_t* Mt, T* Yrec_t, int tb, int te, int group, int lane) {
-    if (role == Q) {
-        role_pass<R, Q, T>(p, sh, ebuf, Cs, Yt, Mt, Yrec_t, tb, te, group, lane);
-        return;
-    }
-    if constexpr (Q + 1 < nsplit_for(R)) dispatch_pass<R, T, Q + 1>(role, p, sh, ebuf, Cs, Yt, Mt, Yrec_t, tb, te, group, lane);
-}
-template <int R, typename T, int Q>
-__device__ __forceinline__ void dispatch_flush(int role, Smem<R>& sh, const double* ebuf, T* Cs, int tb, int te,
-                                               int group, int lane) {
-    if (role == Q) {
-        role_flush<R, Q, T>(sh, ebuf, Cs, tb, te, group, lane);
-        return;
-    }
-    if constexpr (Q + 1 < nsplit_for(R)) dispatch_flush<R, T, Q + 1>(role, sh, ebuf, Cs, tb, te, group, lane);
+    constexpr int NV = R + 4;
+    int base = 0, lim = NV;
+    bfly<NV, 16, NV>(A.v, lane, base, lim);
+    constexpr int NF = bfly_final(NV);
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+        if (base + i < lim) red[ngram(R) + base + i] = A.v[i];
 }
 
 // ---- predict half: x_bar = f(x), P_bar = F P F' + Q, V x_bar, a (all `nthr` threads; ends with a barrier) ----
@@ -292,7 +276,7 @@ __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, i
 // the unused row of largest |a_ik| (every thread finds it redundantly -> no broadcast barrier) and
 // perm[k] remembers it, so the solution row of unknown k is aug[R & 1][perm[k]].
 template <int R>
-__device__ void gauss_jordan_cta(Smem<R>& sh, int tid, int nthr) {
+__device__ void gauss_jordan_cta(Smem<R>& sh, int tid, int nthr) {   // nthr = participating threads (barrier 1)
     constexpr int NC = 2 * R + 1;
     unsigned used = 0;
     for (int k = 0; k < R; ++k) {
@@ -315,7 +299,7 @@ __device__ void gauss_jordan_cta(Smem<R>& sh, int tid, int nthr) {
             }
         }
         const int pi = ix[0];
-        const double inv = 1.0 / sh.aug[cur][pi][k];
+        const double inv = fast_rcp(sh.aug[cur][pi][k]);
         used |= 1u << pi;
         if (tid == 0) sh.perm[k] = pi;
         for (int idx = tid; idx < R * NC; idx += nthr) {
@@ -325,7 +309,7 @@ __device__ void gauss_jordan_cta(Smem<R>& sh, int tid, int nthr) {
             const double aik = sh.aug[cur][i][k];
             sh.aug[nxt][i][c] = (i == pi) ? rpc : fma(-aik, rpc, aic);
         }
-        sync_n(nthr);
+        named_bar_sync(1, nthr);
     }
 }
 
@@ -358,7 +342,11 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
             sh.aug[0][i][2 * R] = acc;
         }
         sync_n(nthr);
-        gauss_jordan_cta<R>(sh, tid, nthr);              // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
+        // the elimination is latency-bound: a subset of the warps runs it (less redundant pivot-search work on
+        // the fp64 pipe, cheaper barrier), the others wait at the CTA barrier below
+        const int ngj = nthr < 192 ? nthr : 192;
+        if (tid < ngj) gauss_jordan_cta<R>(sh, tid, ngj);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
+        sync_n(nthr);
     }
     stamp(p, t, 7);
     if (warp == 0) {
@@ -501,22 +489,24 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, Smem<R>& sh, int t
     sync_n(nthr);
 }
 
+// ---- direct-load persistent kernel: C tiles are read from / written to global memory by the warp that
+// owns them; general fallback (any alignment, any d) and the path for small problems / batched series ----
 template <int R, typename T>
-__global__ void __launch_bounds__(nsplit_for(R) * ngroups_for(R) * 32, 1) psmf_filter_kernel(const KParams p) {
-    constexpr int NS = nsplit_for(R), NG = ngroups_for(R), NSP = nstat_pad(R), NST = nstat(R);
+__global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KParams p) {
+    constexpr int NW = V1_WARPS, NSP = nstat_pad(R), NST = nstat(R);
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ Smem<R> sh;
-    double* ebuf = reinterpret_cast<double*>(dyn_smem);
+    double* stage_all = reinterpret_cast<double*>(dyn_smem);                   // NW staging tiles [R][32] fp64
+    double* ebuf = stage_all + NW * R * TILE;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int group = warp / NS;
-    const int role = ((warp % NS) + group) % NS;      // spread the roles over the 4 SM sub-partitions
     const int series = blockIdx.x / p.cps;
     const int part = blockIdx.x % p.cps;
     const int ntiles = (int)((p.d + TILE - 1) / TILE);
     const int tb = (int)((int64_t)ntiles * part / p.cps);
     const int te = (int)((int64_t)ntiles * (part + 1) / p.cps);
     const bool writer = part == 0;
+    double* stage = stage_all + warp * R * TILE;
 
     T* Cs = reinterpret_cast<T*>(p.C) + (int64_t)series * p.c_series_stride;
     double* stg = p.state + (int64_t)series * st_size(R);
@@ -540,19 +530,47 @@ __global__ void __launch_bounds__(nsplit_for(R) * ngroups_for(R) * 32, 1) psmf_f
     predict_cta<R>(p, sh, tid, p.k0, series, blockDim.x);
 
     for (int64_t t = 0; t < p.n_steps; ++t) {
-        const T* Yt = reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst + t * p.ldy;
-        const uint8_t* Mt = p.M ? p.M + (int64_t)series * p.msst + t * p.ldm : nullptr;
+        const T* __restrict__ Yt = reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst + t * p.ldy;
+        const uint8_t* __restrict__ Mt = p.M ? p.M + (int64_t)series * p.msst + t * p.ldm : nullptr;
         T* Yrec_t = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + t * p.ldrec : nullptr;
         stamp(p, t, 0);
-        dispatch_pass<R, T, 0>(role, p, sh, ebuf, Cs, Yt, Mt, Yrec_t, tb, te, group, lane);
+        const double w1 = sh.w1, w0 = sh.w0;
+        TileAcc<R> acc;
+        acc.zero();
+        for (int tile = tb + warp; tile < te; tile += NW) {
+            const int64_t row = (int64_t)tile * TILE + lane;
+            const int rl = (tile - tb) * TILE + lane;
+            T* gt = Cs + (int64_t)tile * (R * TILE);
+            double c[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) c[j] = (double)gt[tile_pos(j, lane)];
+            const double ep = ebuf[rl];
+            const bool inb = row < p.d;
+            bool mi = inb;
+            if (Mt != nullptr && inb) mi = Mt[row] != 0;
+            const double yi = inb ? (double)Yt[row] : 0.0;
+            double e, yh;
+            row_stats<R>(acc, sh, c, ep, inb, mi, yi, w1, w0, e, yh);
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                gt[tile_pos(j, lane)] = (T)c[j];
+                stage[tile_pos(j, lane)] = c[j];
+            }
+            ebuf[rl] = e;
+            if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
+            const unsigned mbits = __ballot_sync(FULL, mi);
+            __syncwarp();
+            tile_gram<R, double>(acc, stage, mbits, lane);
+            __syncwarp();
+        }
+        acc_writeout<R>(acc, sh.red + warp * NSP, w1, lane);
         stamp(p, t, 1);
         __syncthreads();
         stamp(p, t, 2);
-        // CTA partial: fixed order over the row groups
-        if (tid < NST) {
+        if (tid < NST) {                                   // CTA partial: fixed order over the warps
             double s = 0.0;
 #pragma unroll
-            for (int g = 0; g < NG; ++g) s += sh.red[g * NSP + tid];
+            for (int w = 0; w < NW; ++w) s += sh.red[w * NSP + tid];
             sh.part[tid] = s;
         }
         grid_reduce<R>(p, sh, tid, lane, warp, t, series, part, blockDim.x);
@@ -561,7 +579,14 @@ __global__ void __launch_bounds__(nsplit_for(R) * ngroups_for(R) * 32, 1) psmf_f
         stamp(p, t, 6);
     }
 
-    dispatch_flush<R, T, 0>(role, sh, ebuf, Cs, tb, te, group, lane);
+    // apply the pending rank-1 update of the last step so that C in HBM is the filtered C_T
+    for (int tile = tb + warp; tile < te; tile += NW) {
+        const int rl = (tile - tb) * TILE + lane;
+        T* gt = Cs + (int64_t)tile * (R * TILE);
+        const double ep = ebuf[rl];
+#pragma unroll
+        for (int j = 0; j < R; ++j) gt[tile_pos(j, lane)] = (T)fma(ep, sh.g[j], (double)gt[tile_pos(j, lane)]);
+    }
     if (writer) {
         for (int i = tid; i < R * R; i += blockDim.x) {
             stg[st_P(R) + i] = sh.P[i];

@@ -13,7 +13,7 @@ namespace psmf {
 template <typename T>
 static cudaError_t launch_t(const KParams& p, int grid, size_t dyn, cudaStream_t st, bool coop) {
     auto kern = psmf_filter_kernel<PSMF_R, T>;
-    constexpr int threads = nsplit_for(PSMF_R) * ngroups_for(PSMF_R) * 32;
+    constexpr int threads = V1_WARPS * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     if (coop) {
@@ -28,7 +28,7 @@ static cudaError_t launch_t(const KParams& p, int grid, size_t dyn, cudaStream_t
 template <typename T>
 static cudaError_t shape_t(size_t dyn, LaunchShape* out) {
     auto kern = psmf_filter_kernel<PSMF_R, T>;
-    constexpr int threads = nsplit_for(PSMF_R) * ngroups_for(PSMF_R) * 32;
+    constexpr int threads = V1_WARPS * 32;
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, kern);
     if (e != cudaSuccess) return e;

@@ -23,33 +23,12 @@ namespace psmf {
 
 constexpr int MAXSLOT = 64;
 
-__host__ __device__ constexpr int s_nsplit(int R) { return R <= 6 ? 1 : (R <= 10 ? 2 : 5); }
-__host__ __device__ constexpr int s_ngroups(int R) { return R <= 6 ? 8 : (R <= 10 ? 6 : 3); }
-__host__ __device__ constexpr int s_tiles_per_chunk(int R) { return 2 * s_ngroups(R); }
-__host__ __device__ constexpr int s_threads(int R) { return (s_nsplit(R) * s_ngroups(R) + 1) * 32; }
-
-// Gram rows owned by role q: boundaries minimising max(2*accumulators + 2*columns) per role, then FMAs
-// (computed offline; role 0 also carries y_hat / e / b / s / q1 / q0 / n_obs).
-__host__ __device__ constexpr int s_split_begin(int R, int q) {
-    const int NS = s_nsplit(R);
-    if (q <= 0) return 0;
-    if (q >= NS) return R;
-    if (NS == 2) return R <= 8 ? 1 : 2;
-    // NS == 5, R in 11..16
-    switch (R) {
-        case 11: { const int b[6] = {0, 1, 2, 3, 4, 11}; return b[q]; }
-        case 12: { const int b[6] = {0, 1, 2, 3, 5, 12}; return b[q]; }
-        case 13: { const int b[6] = {0, 1, 2, 3, 6, 13}; return b[q]; }
-        case 14: { const int b[6] = {0, 1, 2, 3, 6, 14}; return b[q]; }
-        case 15: { const int b[6] = {0, 1, 2, 4, 7, 15}; return b[q]; }
-        default: { const int b[6] = {0, 1, 3, 5, 8, 16}; return b[q]; }
-    }
-}
+__host__ __device__ constexpr int s_threads() { return (V2_CWARPS + 1) * 32; }
 
 __host__ __device__ constexpr size_t round128(size_t x) { return (x + 127) / 128 * 128; }
 template <int R, typename T>
 struct SlotLayout {
-    static constexpr int TS = s_tiles_per_chunk(R);
+    static constexpr int TS = V2_TS;
     static constexpr size_t TILE_BYTES = (size_t)R * TILE * sizeof(T);
     static constexpr size_t CB = round128(TS * TILE_BYTES);
     static constexpr size_t YB = round128((size_t)TS * TILE * sizeof(T));
@@ -64,6 +43,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -107,120 +89,64 @@ __device__ __forceinline__ void bulk_wait() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- consumer: one role over all chunks of one pass ----------------------------------------------------
+// ---- consumer: one warp over its tiles of one pass (tile tl of the CTA belongs to warp tl % V2_CWARPS) ----
 // FLUSH: apply the pending rank-1 update only (the pass after the last step).
-template <int R, int Q, typename T, bool FLUSH>
-__device__ __forceinline__ void s_role_pass(const KParams& p, Smem<R>& sh, double* __restrict__ ebuf,
+template <int R, typename T, bool FLUSH>
+__device__ __forceinline__ void s_warp_pass(const KParams& p, Smem<R>& sh, double* __restrict__ ebuf,
                                             unsigned char* __restrict__ slots, uint64_t* full, uint64_t* done,
                                             T* __restrict__ Yrec_t, bool masked, int tb, int nt, int nslot, int64_t pass,
-                                            int group, int lane) {
+                                            int warp, int lane) {
     using L = SlotLayout<R, T>;
-    constexpr int NS = s_nsplit(R), NG = s_ngroups(R), NSP = nstat_pad(R), TS = L::TS;
-    constexpr int JB = s_split_begin(R, Q), JE = s_split_begin(R, Q + 1);
-    constexpr int NGR = gram_off(R, JE) - gram_off(R, JB);
-    constexpr int NACC = FLUSH ? 1 : NGR + (Q == 0 ? R + 4 : 0);
+    constexpr int NSP = nstat_pad(R), TS = L::TS;
     const double w1 = sh.w1, w0 = sh.w0;
     const int nchunks = (nt + TS - 1) / TS;
     const bool streaming = nchunks > nslot;
-    double acc[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    TileAcc<R> acc;
+    acc.zero();
 
-    for (int k = 0; k < nchunks; ++k) {
+    for (int tl = warp; tl < nt; tl += V2_CWARPS) {
+        const int k = tl / TS, i = tl - k * TS;
         const int64_t kk = pass * nchunks + k;
         const int slot = streaming ? (int)(kk % nslot) : k;
         const uint32_t parity = (uint32_t)((streaming ? kk / nslot : pass) & 1);
         unsigned char* sb = slots + (size_t)slot * L::SLOT;
         mbar_wait(&full[slot], parity);
-        const int ntc = min(TS, nt - k * TS);
-        for (int i = group; i < ntc; i += NG) {
-            const int tl = k * TS + i;                                   // tile index inside the CTA
-            const int64_t row = (int64_t)(tb + tl) * TILE + lane;
-            const int rl = tl * TILE + lane;
-            T* ct = reinterpret_cast<T*>(sb) + (size_t)i * (R * TILE) + lane;
-            if constexpr (FLUSH) {
-                const double ep = ebuf[rl];
+        const int64_t row = (int64_t)(tb + tl) * TILE + lane;
+        const int rl = tl * TILE + lane;
+        T* tile = reinterpret_cast<T*>(sb) + (size_t)i * (R * TILE);
+        const double ep = ebuf[rl];
+        if constexpr (FLUSH) {
 #pragma unroll
-                for (int j = JB; j < JE; ++j) ct[j * TILE] = (T)fma(ep, sh.g[j], (double)ct[j * TILE]);
-            } else {
+            for (int j = 0; j < R; ++j) tile[tile_pos(j, lane)] = (T)fma(ep, sh.g[j], (double)tile[tile_pos(j, lane)]);
+        } else {
             double c[R];
 #pragma unroll
-            for (int j = JB; j < R; ++j) c[j] = (double)ct[j * TILE];
-            const double ep = ebuf[rl];
+            for (int j = 0; j < R; ++j) c[j] = (double)tile[tile_pos(j, lane)];
             const bool inb = row < p.d;
             bool mi = inb;
             if (masked && inb) mi = (sb + L::CB + L::YB)[i * TILE + lane] != 0;
-            double yi = 0.0;
-            if (Q == 0 && inb) yi = (double)reinterpret_cast<const T*>(sb + L::CB)[i * TILE + lane];
-            if (NS > 1) named_bar_sync(1 + group, NS * 32);
+            const double yi = inb ? (double)reinterpret_cast<const T*>(sb + L::CB)[i * TILE + lane] : 0.0;
+            double e, yh;
+            row_stats<R>(acc, sh, c, ep, inb, mi, yi, w1, w0, e, yh);
 #pragma unroll
-            for (int j = JB; j < R; ++j) c[j] = fma(ep, sh.g[j], c[j]);      // rPSMF.py:111 (previous step)
-#pragma unroll
-            for (int j = JB; j < JE; ++j) ct[j * TILE] = (T)c[j];
-            const double w = mi ? w1 : w0;                                    // rPSMF.py:92,98,32
-            const double mw = mi ? w1 : 0.0;
-#pragma unroll
-            for (int j = JB; j < JE; ++j) {
-                const double cw = c[j] * mw;
-#pragma unroll
-                for (int k2 = j; k2 < R; ++k2) {
-                    const int idx = gram_off(R, j) - gram_off(R, JB) + (k2 - j);
-                    acc[idx] = fma(cw, c[k2], acc[idx]);                      // G = CM' Ri CM, rPSMF.py:35
-                }
-            }
-            if (Q == 0) {
-                double yh4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int j = 0; j < R; ++j) yh4[j & 3] = fma(c[j], sh.xb[j], yh4[j & 3]);   // rPSMF.py:89
-                const double yh = (yh4[0] + yh4[1]) + (yh4[2] + yh4[3]);
-                const double e = yi - (mi ? yh : 0.0);                        // rPSMF.py:101
-                ebuf[rl] = e;
-                if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
-                const double ew = e * mw;
-#pragma unroll
-                for (int j = 0; j < R; ++j) acc[NGR + j] = fma(ew, c[j], acc[NGR + j]);
-                const double e2 = e * e;
-                acc[NGR + R + 0] = fma(inb ? w : 0.0, e2, acc[NGR + R + 0]);
-                acc[NGR + R + 1] += mi ? e2 : 0.0;
-                acc[NGR + R + 2] += mi ? 0.0 : e2;
-                acc[NGR + R + 3] += mi ? 1.0 : 0.0;
-            }
-            }  // !FLUSH
+            for (int j = 0; j < R; ++j) tile[tile_pos(j, lane)] = (T)c[j];
+            ebuf[rl] = e;
+            if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
+            const unsigned mbits = __ballot_sync(FULL, mi);
+            __syncwarp();
+            tile_gram<R, T>(acc, tile, mbits, lane);
         }
-        // this warp is done with the slot: make its generic-proxy writes visible to the bulk store
+        // this warp is done with its tile: make the generic-proxy writes visible to the bulk store and
+        // release the slot (the warp that owns the last tile of a partial chunk also signs for the
+        // tiles that do not exist)
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&done[slot]);
-    }
-    if (FLUSH) return;
-
-    int base = 0, lim = NACC;
-    bfly<NACC, 16, NACC>(acc, lane, base, lim);
-    constexpr int NF = bfly_final(NACC);
-#pragma unroll
-    for (int i = 0; i < NF; ++i) {
-        const int li = base + i;
-        if (li < lim) {
-            int gi;
-            if (Q == 0)
-                gi = li < NGR ? li : ngram(R) + (li - NGR);
-            else
-                gi = gram_off(R, JB) + li;
-            sh.red[group * NSP + gi] = acc[i];
+        if (lane == 0) {
+            const int ntc = min(TS, nt - k * TS);
+            mbar_arrive_n(&done[slot], (i == ntc - 1) ? (uint32_t)(TS - ntc + 1) : 1u);
         }
     }
-}
-
-template <int R, typename T, bool FLUSH, int Q>
-__device__ __forceinline__ void s_dispatch(int role, const KParams& p, Smem<R>& sh, double* ebuf, unsigned char* slots,
-                                           uint64_t* full, uint64_t* done, T* Yrec_t, bool masked, int tb, int nt,
-                                           int nslot, int64_t pass, int group, int lane) {
-    if (role == Q) {
-        s_role_pass<R, Q, T, FLUSH>(p, sh, ebuf, slots, full, done, Yrec_t, masked, tb, nt, nslot, pass, group, lane);
-        return;
-    }
-    if constexpr (Q + 1 < s_nsplit(R))
-        s_dispatch<R, T, FLUSH, Q + 1>(role, p, sh, ebuf, slots, full, done, Yrec_t, masked, tb, nt, nslot, pass, group, lane);
+    if constexpr (!FLUSH) acc_writeout<R>(acc, sh.red + warp * NSP, w1, lane);
 }
 
 // ---- producer: one thread drives all bulk copies of the CTA -------------------------------------------
@@ -296,10 +222,10 @@ __device__ void s_producer(const KParams& p, unsigned char* slots, uint64_t* ful
 }
 
 template <int R, typename T>
-__global__ void __launch_bounds__(s_threads(R), 1) psmf_stream_kernel(const KParams p) {
+__global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KParams p) {
     using L = SlotLayout<R, T>;
-    constexpr int NS = s_nsplit(R), NG = s_ngroups(R), NSP = nstat_pad(R), NST = nstat(R);
-    constexpr int NCW = NS * NG, NCT = NCW * 32;
+    constexpr int NSP = nstat_pad(R), NST = nstat(R);
+    constexpr int NCW = V2_CWARPS, NCT = NCW * 32;
     extern __shared__ __align__(128) unsigned char dyn_smem_s[];
     __shared__ Smem<R> sh;
     __shared__ __align__(8) uint64_t full[MAXSLOT];
@@ -323,7 +249,7 @@ __global__ void __launch_bounds__(s_threads(R), 1) psmf_stream_kernel(const KPar
     if (tid == 0) {
         for (int s = 0; s < nslot; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&done[s], NCW);
+            mbar_init(&done[s], L::TS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -350,22 +276,20 @@ __global__ void __launch_bounds__(s_threads(R), 1) psmf_stream_kernel(const KPar
     }
 
     // ---- consumer warps ----
-    const int group = warp / NS;
-    const int role = ((warp % NS) + group) % NS;
     const bool masked = p.M != nullptr;
     predict_cta<R>(p, sh, tid, p.k0, series, NCT);
 
     for (int64_t t = 0; t < p.n_steps; ++t) {
         T* Yrec_t = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + t * p.ldrec : nullptr;
         stamp(p, t, 0);
-        s_dispatch<R, T, false, 0>(role, p, sh, ebuf, slots, full, done, Yrec_t, masked, tb, nt, nslot, t, group, lane);
+        s_warp_pass<R, T, false>(p, sh, ebuf, slots, full, done, Yrec_t, masked, tb, nt, nslot, t, warp, lane);
         stamp(p, t, 1);
         sync_n(NCT);
         stamp(p, t, 2);
-        if (tid < NST) {
+        if (tid < NST) {                     // CTA partial: fixed order over the warps
             double s = 0.0;
 #pragma unroll
-            for (int g = 0; g < NG; ++g) s += sh.red[g * NSP + tid];
+            for (int w = 0; w < NCW; ++w) s += sh.red[w * NSP + tid];
             sh.part[tid] = s;
         }
         grid_reduce<R>(p, sh, tid, lane, warp, t, series, part, NCT);
@@ -375,7 +299,7 @@ __global__ void __launch_bounds__(s_threads(R), 1) psmf_stream_kernel(const KPar
     }
 
     // flush pass: pending rank-1 update of the last step
-    s_dispatch<R, T, true, 0>(role, p, sh, ebuf, slots, full, done, (T*)nullptr, masked, tb, nt, nslot, p.n_steps, group, lane);
+    s_warp_pass<R, T, true>(p, sh, ebuf, slots, full, done, (T*)nullptr, masked, tb, nt, nslot, p.n_steps, warp, lane);
     if (writer) {
         for (int i = tid; i < R * R; i += NCT) {
             stg[st_P(R) + i] = sh.P[i];
