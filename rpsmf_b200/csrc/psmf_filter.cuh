@@ -271,45 +271,53 @@ __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, i
     sync_n(nthr);
 }
 
-// Gauss-Jordan with partial pivoting on the R x (2R+1) augmented matrix [I + Pbar G | Pbar | Pbar b], one
-// element per thread and one barrier per elimination step.  Rows are not swapped: step k eliminates with
-// the unused row of largest |a_ik| (every thread finds it redundantly -> no broadcast barrier) and
-// perm[k] remembers it, so the solution row of unknown k is aug[R & 1][perm[k]].
+// Gauss-Jordan with partial pivoting on the R x (2R+1) augmented matrix [I + Pbar G | Pbar | Pbar b], run by
+// GJ_THREADS threads with one named barrier per elimination step.  Thread (row i, q) keeps its <= CPT
+// elements of row i in registers; the matrix is double-buffered in shared memory so that everybody can read
+// column k and the pivot row of the previous step.  Rows are not swapped: step k eliminates with the unused
+// row of largest |a_ik| -- found redundantly by every warp (no broadcast barrier) with one warp-wide
+// integer max over the high words of |a_ik| (16 mantissa bits decide, ties -> lowest row) -- and perm[k]
+// remembers it, so the solution row of unknown k is aug[R & 1][perm[k]].
+constexpr int GJ_THREADS = 192;
 template <int R>
-__device__ void gauss_jordan_cta(Smem<R>& sh, int tid, int nthr) {   // nthr = participating threads (barrier 1)
+__device__ void gauss_jordan_cta(Smem<R>& sh, int tid) {
     constexpr int NC = 2 * R + 1;
+    constexpr int TPR = GJ_THREADS / R;                 // threads per row
+    constexpr int CPT = (NC + TPR - 1) / TPR;           // columns per thread
+    const bool active = tid < R * TPR;
+    const int i = active ? tid / TPR : 0;
+    const int q = tid - (tid / TPR) * TPR;
+    double own[CPT];
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) {
+        const int c = q + TPR * e;
+        own[e] = (active && c < NC) ? sh.aug[0][i][c] : 0.0;
+    }
     unsigned used = 0;
+    const int r2 = tid & 15;                            // pivot search: lane -> candidate row (both half-warps)
     for (int k = 0; k < R; ++k) {
         const int cur = k & 1, nxt = cur ^ 1;
-        double v[R];
-        int ix[R];
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-            v[i] = ((used >> i) & 1u) ? -1.0 : fabs(sh.aug[cur][i][k]);
-            ix[i] = i;
-        }
-#pragma unroll
-        for (int st = 1; st < R; st <<= 1) {
-#pragma unroll
-            for (int i = 0; i + st < R; i += 2 * st) {
-                if (v[i + st] > v[i]) {                 // strict: ties keep the lower row index
-                    v[i] = v[i + st];
-                    ix[i] = ix[i + st];
-                }
-            }
-        }
-        const int pi = ix[0];
-        const double inv = fast_rcp(sh.aug[cur][pi][k]);
+        // every warp finds the pivot row on its own: one candidate per lane, integer max over the high word
+        // of |a_ik| (REDUX), and the reciprocal of every candidate is computed while the max is in flight
+        const double cand = (r2 < R) ? sh.aug[cur][r2][k] : 1.0;
+        const double aik = sh.aug[cur][i][k];
+        const int hi = __double2hiint(fabs(cand));
+        const int key = (r2 >= R || ((used >> r2) & 1u)) ? -1 : ((hi & 0x7ffffff0) | (15 - r2));
+        const double cinv = fast_rcp(cand);
+        const int pi = 15 - (__reduce_max_sync(FULL, key) & 15);
+        const double inv = __shfl_sync(FULL, cinv, pi);
         used |= 1u << pi;
         if (tid == 0) sh.perm[k] = pi;
-        for (int idx = tid; idx < R * NC; idx += nthr) {
-            const int i = idx / NC, c = idx - i * NC;
-            const double rpc = sh.aug[cur][pi][c] * inv;
-            const double aic = sh.aug[cur][i][c];
-            const double aik = sh.aug[cur][i][k];
-            sh.aug[nxt][i][c] = (i == pi) ? rpc : fma(-aik, rpc, aic);
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) {
+            const int c = q + TPR * e;
+            if (active && c < NC) {
+                const double rpc = sh.aug[cur][pi][c] * inv;
+                own[e] = (i == pi) ? rpc : fma(-aik, rpc, own[e]);
+                sh.aug[nxt][i][c] = own[e];
+            }
         }
-        named_bar_sync(1, nthr);
+        named_bar_sync(1, GJ_THREADS);
     }
 }
 
@@ -344,8 +352,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         sync_n(nthr);
         // the elimination is latency-bound: a subset of the warps runs it (less redundant pivot-search work on
         // the fp64 pipe, cheaper barrier), the others wait at the CTA barrier below
-        const int ngj = nthr < 192 ? nthr : 192;
-        if (tid < ngj) gauss_jordan_cta<R>(sh, tid, ngj);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
+        if (tid < GJ_THREADS) gauss_jordan_cta<R>(sh, tid);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
         sync_n(nthr);
     }
     stamp(p, t, 7);
