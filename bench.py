@@ -247,7 +247,7 @@ def main():
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                     peak_source="MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                     algorithmic_bytes_per_filter_step=algorithmic_bytes_per_filter_step(d_loc, r, esize),
-                    kernel="psmf_filter_kernel<%d,%s>" % (r, "double" if esize == 8 else "float"),
+                    kernel="%s<%d,%s>" % ("psmf_stream_kernel" if info.get("kernel") == "tma" else "psmf_filter_kernel", r, "double" if esize == 8 else "float"),
                     mean_launch_ms=float(np.mean(per_launch_ms)))
 
     # end-to-end through the public API with HOST buffers (pinned), H2D inside the timed region
