@@ -47,6 +47,8 @@ typedef struct psmf_engine* psmf_handle;
 #define PSMF_SIMPLIFIED    2   /* ExperimentSynthetic overrides: P_bar=P, eta=tr(R)/d, x_t=x_bar (synthetic_psmf.py:78-100) */
 #define PSMF_CUPDATE_VT    4   /* C += e (V x)'/N  (rPSMF.py:111, psmf.py:132); unset: C += e (V' x)'/N (PSMF.py:80) */
 #define PSMF_FIXED_LAMBDA  16  /* rpsmf.py:36-40 */
+#define PSMF_LL_STUDENT    32  /* theta gradient of the Student-t incremental likelihood (rpsmf.py:62-71); unset: Gaussian
+                               * form (psmf.py:57-64; with a mask: rpsmf.py:196-200)                                   */
 
 /* dynamics f_theta(x, k) of the predict half (psmf.py:104-115) */
 #define PSMF_DYN_IDENTITY 0    /* RandomWalk, nonlinearities.py:42-56; Impute scripts */
@@ -102,6 +104,8 @@ typedef struct psmf_io {
     double*        scal_out;   /* (n_series, n_steps, PSMF_NSCAL) or NULL                             */
     const double*  xbar_ext;   /* PSMF_DYN_EXTERNAL: (n_series, r)                                    */
     const double*  F_ext;      /* PSMF_DYN_EXTERNAL: (n_series, r, r) row-major                       */
+    double*        grad_out;   /* (n_series, r) sum over the run of d ell_k / d theta (PSMF_DYN_COS), or NULL
+                                * (_store_gradient, psmf.py:167-177)                                     */
 } psmf_io;
 
 /* lifecycle ------------------------------------------------------------------------------------ */

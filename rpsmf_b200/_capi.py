@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpsmf_b200.so")
 
 F64, F32 = 0, 1
-ROBUST, SIMPLIFIED, CUPDATE_VT, FIXED_LAMBDA = 1, 2, 4, 16
+ROBUST, SIMPLIFIED, CUPDATE_VT, FIXED_LAMBDA, LL_STUDENT = 1, 2, 4, 16, 32
 DYN_IDENTITY, DYN_COS, DYN_EXTERNAL = 0, 1, 3
 NSCAL = 8
 SCAL_NAMES = ("a", "eta", "N", "omega", "phi", "sSe", "lam", "rho")
@@ -42,7 +42,7 @@ class PsmfIO(C.Structure):
         ("X_out", C.c_void_p),
         ("Yrec_out", C.c_void_p), ("ldrec", C.c_int64), ("rec_series_stride", C.c_int64),
         ("scal_out", C.c_void_p),
-        ("xbar_ext", C.c_void_p), ("F_ext", C.c_void_p),
+        ("xbar_ext", C.c_void_p), ("F_ext", C.c_void_p), ("grad_out", C.c_void_p),
     ]
 
 

@@ -330,6 +330,7 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     p.Yrec = io->Yrec_out; p.ldrec = io->ldrec; p.recsst = io->rec_series_stride;
     p.scal_out = io->scal_out;
     p.xbar_ext = io->xbar_ext; p.F_ext = io->F_ext;
+    p.grad_out = io->grad_out;
     p.partials = h->partials;
     p.bar = h->bar;
     p.status = h->status;

@@ -20,7 +20,7 @@ constexpr int MAXR = 16;
 constexpr int MAX_PEERS = 8;
 
 // flags (mirror include/psmf_b200.h)
-constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16;
+constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16, F_LL_STUDENT = 32;
 constexpr int DYN_IDENTITY = 0, DYN_COS = 1, DYN_EXTERNAL = 3;
 
 // ---- tile layout and statistics vector ------------------------------------------------------------
@@ -62,6 +62,7 @@ struct KParams {
     void* Yrec; int64_t ldrec; int64_t recsst;
     double* scal_out;
     const double* xbar_ext; const double* F_ext;
+    double* grad_out;         // (n_series, R) accumulated theta gradient or nullptr
     double* partials;         // [2][ctas][nstat_pad]
     unsigned long long* bar;  // grid barrier counter (monotonic within a launch)
     long long* status;        // first bad step or -1

@@ -44,6 +44,7 @@ struct Smem {
     double a, rho, lam;
     double w1, w0;                 // 1/(rho + a), 1/a : the only two values of w_i (rPSMF.py:92,98,32)
     double sc[8];                  // omega, eta, N, phi, sSe, alpha*phi, beta*omega
+    double grad[R];                // running sum of d ell_k / d theta over the launch
     int perm[R];                   // pivot row of elimination step k
 };
 
@@ -397,6 +398,21 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         if (lane < R) {
             sh.x[lane] = xn;
             if (writer && p.X_out != nullptr) p.X_out[((int64_t)series * p.n_steps + t) * R + lane] = xn;
+            if (p.grad_out != nullptr && p.dynamics == DYN_COS) {
+                // d ell_k / d theta = J_theta' d ell_k / d f with f = x_bar, s = f'Vf + eta = N, e = y - M C f
+                // (psmf.py:57-64,167-177; rpsmf.py:62-71,196-200); C'Me = b (rho + a), n = n_obs, q = q1
+                const double vsf = 0.5 * (sh.vx[lane] + sh.vxt[lane]);
+                const double cte = tot[NGm + lane] * (rho + a);
+                double gf;
+                if ((p.flags & F_LL_STUDENT) != 0) {
+                    const double gq = 1.0 + q1 / (lam * N);
+                    gf = nobs * vsf / N - (nobs + lam) / (gq * lam * N) * (cte + (q1 / N) * vsf);
+                } else {
+                    gf = (nobs / N - q1 / (N * N)) * vsf - cte / N;
+                }
+                const double kabs = (double)(p.k0 + t);
+                sh.grad[lane] += gf * (6.283185307179586 * kabs * sh.fd[lane]);   // J_theta = diag(-2 pi k sin(.))
+            }
         }
         if (lane == 0) {
             sh.sc[0] = omega; sh.sc[1] = eta; sh.sc[2] = N; sh.sc[3] = phi; sh.sc[4] = sSe;
@@ -527,6 +543,7 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
         sh.x[tid] = stg[st_x(R) + tid];
         sh.th[tid] = stg[st_theta(R) + tid];
         sh.g[tid] = 0.0;
+        sh.grad[tid] = 0.0;
     }
     if (tid == 0) {
         sh.rho = stg[st_rho(R)];
@@ -600,7 +617,10 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
             stg[st_V(R) + i] = sh.V[i];
             stg[st_Q(R) + i] = sh.Q[i];
         }
-        if (tid < R) stg[st_x(R) + tid] = sh.x[tid];
+        if (tid < R) {
+            stg[st_x(R) + tid] = sh.x[tid];
+            if (p.grad_out != nullptr) p.grad_out[(int64_t)series * R + tid] = sh.grad[tid];
+        }
         if (tid == 0) {
             stg[st_rho(R)] = sh.rho;
             stg[st_lam(R)] = sh.lam;

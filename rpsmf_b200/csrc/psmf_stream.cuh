@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
         sh.x[tid] = stg[st_x(R) + tid];
         sh.th[tid] = stg[st_theta(R) + tid];
         sh.g[tid] = 0.0;
+        sh.grad[tid] = 0.0;
     }
     if (tid == 0) {
         sh.rho = stg[st_rho(R)];
@@ -306,7 +307,10 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
             stg[st_V(R) + i] = sh.V[i];
             stg[st_Q(R) + i] = sh.Q[i];
         }
-        if (tid < R) stg[st_x(R) + tid] = sh.x[tid];
+        if (tid < R) {
+            stg[st_x(R) + tid] = sh.x[tid];
+            if (p.grad_out != nullptr) p.grad_out[(int64_t)series * R + tid] = sh.grad[tid];
+        }
         if (tid == 0) {
             stg[st_rho(R)] = sh.rho;
             stg[st_lam(R)] = sh.lam;

@@ -28,8 +28,8 @@ class FilterEngine:
     """
 
     def __init__(self, d, r, *, n_series=1, dtype=torch.float64, robust=True, simplified=False,
-                 c_update_transpose=True, fixed_lambda=False, dynamics=_capi.DYN_IDENTITY, alpha=1.0, beta=1.0,
-                 device=None, d_global=None, world_size=1, rank=0, ctas=0, kernel=0):
+                 c_update_transpose=True, fixed_lambda=False, ll_student=False, dynamics=_capi.DYN_IDENTITY, alpha=1.0,
+                 beta=1.0, device=None, d_global=None, world_size=1, rank=0, ctas=0, kernel=0):
         if not torch.cuda.is_available():
             raise RuntimeError("rpsmf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         if dtype not in (torch.float64, torch.float32):
@@ -43,6 +43,7 @@ class FilterEngine:
         flags |= _capi.SIMPLIFIED if simplified else 0
         flags |= _capi.CUPDATE_VT if c_update_transpose else 0
         flags |= _capi.FIXED_LAMBDA if fixed_lambda else 0
+        flags |= _capi.LL_STUDENT if ll_student else 0
         cfg = _capi.PsmfConfig(
             d=self.d, d_global=int(d_global or d), r=self.r, n_series=self.S,
             dtype=_capi.F64 if dtype == torch.float64 else _capi.F32, flags=flags, dynamics=int(dynamics),
@@ -119,7 +120,7 @@ class FilterEngine:
 
     # -- the hot path ------------------------------------------------------------------------------
     def run(self, Y, M=None, k0=1, want_X=True, want_Yrec=False, want_scal=False, xbar=None, F=None,
-            X_out=None, Yrec_out=None, scal_out=None):
+            X_out=None, Yrec_out=None, scal_out=None, want_grad=False):
         """Filter ``T`` steps.  Y: device tensor (T, d) or (S, T, d) in the engine dtype (last dim may be
         padded: ld = stride of the time axis); M: uint8 tensor of the same shape or None."""
         S, d, r = self.S, self.d, self.r
@@ -157,6 +158,10 @@ class FilterEngine:
             sc = scal_out if scal_out is not None else torch.empty((S, T, _capi.NSCAL), dtype=torch.float64, device=self.device)
             io.scal_out = sc.data_ptr()
             res["scal"] = sc
+        if want_grad:
+            gr = torch.zeros((S, r), dtype=torch.float64, device=self.device)
+            io.grad_out = gr.data_ptr()
+            res["grad"] = gr
         keep = [Y, M]
         if self.dynamics == _capi.DYN_EXTERNAL:
             xb = _dev_tensor(xbar, torch.float64, self.device).reshape(S, r)

@@ -208,10 +208,40 @@ def make_pypsmf():
     print("wrote pypsmf_cases", os.path.getsize(os.path.join(HERE, "pypsmf_cases.npz")) // 1024, "KiB")
 
 
+def make_recursive():
+    """PSMFRecursive / rPSMFRecursive (psmf.py:275-331, rpsmf.py:290-334): full step, theta updated every
+    `update_every` steps inside the sweep (the reference's gradient comes from the finite-difference shim)."""
+    psmf = ref_loader.pypsmf()
+    data = ref_loader.synthetic_module("data")
+    out = {}
+    d, r, T = 10, 3, 90
+    for tag, robust, ue in (("rec_psmf_1", False, 1), ("rec_psmf_7", False, 7), ("rec_rpsmf_4", True, 4)):
+        np.random.seed(5535)
+        dat = (data.generate_t_data if robust else data.generate_normal_data)(_cosnl, d=d, T=T, n_pred=0, r=r, var=0.1)
+        y = dat["y_train"]
+        Ymat = np.stack([y[k].reshape(d) for k in range(1, T + 1)])
+        C0 = 0.1 * np.random.randn(d, r)
+        theta0 = 0.1 * np.random.rand(r, 1)
+        V0 = 0.1 * np.eye(r); mu0 = 0.2 * np.ones((r, 1)); P0 = 0.3 * np.eye(r); Q = 0.02 * np.eye(r)
+        if robust:
+            o = psmf.rPSMFRecursive(theta0, C0, V0, mu0, P0, Q, np.eye(d), 1.8, _cosnl)
+        else:
+            o = psmf.PSMFRecursive(theta0, C0, V0, mu0, P0, {k: Q for k in range(T + 1)},
+                                   {k: np.eye(d) for k in range(T + 1)}, _cosnl)
+        o.run(y, T, 5, update_every=ue)
+        res = _collect(o, T, d)
+        thetas = np.stack([o._theta[k].reshape(-1) for k in range(T + 1)])
+        ypp = np.stack([np.asarray(o._y_pred[k]).reshape(d) for k in range(T + 1, T + 6)])
+        out.update({tag + "_" + k: v for k, v in dict(Y=Ymat, C0=C0, theta0=theta0.reshape(-1), V0=V0, mu0=mu0.reshape(-1),
+                                                      P0=P0, Q=Q, thetas=thetas, ypred_future=ypp, **res).items()})
+    np.savez_compressed(os.path.join(HERE, "pypsmf_recursive.npz"), **out)
+    print("wrote pypsmf_recursive", os.path.getsize(os.path.join(HERE, "pypsmf_recursive.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found at %s" % REF)
-    which = sys.argv[1:] or ["pm25", "pm10", "sp500", "pypsmf"]
+    which = sys.argv[1:] or ["pm25", "pm10", "sp500", "pypsmf", "recursive"]
     if "pm25" in which:
         make_impute("impute_pm25_30", "LondonAir_PM25.csv", 30, None, 1,
                     published="LondonAir_PM25_30_%s.json")
@@ -221,3 +251,5 @@ if __name__ == "__main__":
         make_impute("impute_sp500_head_30", "sp500_closing_prices.csv", 30, 160, 1)
     if "pypsmf" in which:
         make_pypsmf()
+    if "recursive" in which:
+        make_recursive()

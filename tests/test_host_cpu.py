@@ -1,0 +1,121 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares (no compute calls
+without a GPU), and the host-side logic of the Python surface."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "psmf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(psmf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rpsmf_b200 import _capi
+    names = _header_functions()
+    assert len(names) >= 12
+    assert sorted(_capi.EXPORTS) == names, "rpsmf_b200/_capi.py EXPORTS is out of sync with include/psmf_b200.h"
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for n in names:
+        assert getattr(lib, n) is not None
+    assert _capi.lib().psmf_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    from rpsmf_b200 import _capi
+    # psmf_config: 2 x int64, 10 x int32, 2 x double; psmf_io: 14 pointer/int64 slots
+    assert ctypes.sizeof(_capi.PsmfConfig) == 2 * 8 + 10 * 4 + 2 * 8
+    assert ctypes.sizeof(_capi.PsmfIO) == 14 * 8
+    hdr = open(os.path.join(ROOT, "include", "psmf_b200.h")).read()
+    for flag, val in (("PSMF_ROBUST", _capi.ROBUST), ("PSMF_SIMPLIFIED", _capi.SIMPLIFIED), ("PSMF_CUPDATE_VT", _capi.CUPDATE_VT),
+                      ("PSMF_FIXED_LAMBDA", _capi.FIXED_LAMBDA), ("PSMF_LL_STUDENT", _capi.LL_STUDENT),
+                      ("PSMF_DYN_COS", _capi.DYN_COS), ("PSMF_DYN_EXTERNAL", _capi.DYN_EXTERNAL), ("PSMF_NSCAL", _capi.NSCAL)):
+        m = re.search(r"#define\s+%s\s+(\d+)" % flag, hdr)
+        assert m and int(m.group(1)) == val, flag
+
+
+def test_create_without_gpu_fails_loudly():
+    """No CPU fallback: without a device psmf_create returns an error code and a message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from rpsmf_b200 import _capi, FilterEngine
+    L = _capi.lib()
+    h = ctypes.c_void_p()
+    cfg = _capi.PsmfConfig(d=64, d_global=64, r=4, n_series=1, dtype=0, flags=1, dynamics=0, device=0, world_size=1, rank=0,
+                           ctas=0, kernel=0, alpha=1.0, beta=1.0)
+    rc = L.psmf_create(ctypes.byref(h), ctypes.byref(cfg))
+    assert rc < 0 and not h.value
+    assert L.psmf_last_error(None)
+    with pytest.raises(RuntimeError):
+        FilterEngine(64, 4)
+    bad = _capi.PsmfConfig(d=64, d_global=64, r=17, n_series=1, dtype=0, flags=0, dynamics=0, device=0, world_size=1, rank=0,
+                           ctas=0, kernel=0, alpha=1.0, beta=1.0)
+    assert L.psmf_create(ctypes.byref(h), ctypes.byref(bad)) == -1
+    assert b"rank" in L.psmf_last_error(None)
+
+
+def test_classify_and_jacobian():
+    from rpsmf_b200 import _capi
+    from rpsmf_b200.nonlinearities import RandomWalk, classify, cos_phase, jacobian_x
+    assert classify(RandomWalk(), 3) == _capi.DYN_IDENTITY
+    assert classify(cos_phase, 3) == _capi.DYN_COS
+    assert classify(lambda th, x, t: np.cos(2 * np.pi * th * t + x), 5) == _capi.DYN_COS     # untagged, probed
+    assert classify(lambda th, x, t: x, 2) == _capi.DYN_IDENTITY
+    assert classify(lambda th, x, t: np.tanh(x), 2) == _capi.DYN_EXTERNAL
+    A = np.array([[1.0, 0.2], [-0.3, 0.9]])
+    x = np.array([[0.3], [-0.7]])
+    F = jacobian_x(lambda th, x, t: np.tanh(A @ x), None, x, 1)
+    assert np.allclose(F, (1 - np.tanh(A @ x) ** 2) * A, atol=1e-14)
+    Fd = jacobian_x(lambda th, x, t: np.abs(x) * x, None, x, 1)           # not analytic -> central differences
+    assert np.allclose(Fd, np.diag(2 * np.abs(x).reshape(-1)), atol=1e-6)
+
+
+def test_r_and_q_validation():
+    from rpsmf_b200.impute import _uniform_diag
+    from rpsmf_b200.psmf import _constant_over_k, _uniform_rho
+    assert _uniform_rho(3.0 * np.eye(4), 4, "R") == 3.0
+    assert _uniform_diag(10 * np.eye(5), 5, "R") == 10.0
+    with pytest.raises(NotImplementedError):
+        _uniform_rho(np.diag([1.0, 2.0]), 2, "R")
+    with pytest.raises(NotImplementedError):
+        _uniform_diag(np.array([[1.0, 0.1], [0.1, 1.0]]), 2, "R")
+    Q = np.eye(2)
+    assert _constant_over_k({0: Q, 1: Q, 2: Q.copy()}, "Q") is not None
+    with pytest.raises(NotImplementedError):
+        _constant_over_k({0: Q, 1: 2 * Q}, "Q")
+
+
+def test_hook_override_rejected_without_gpu():
+    from rpsmf_b200 import PSMFIter
+
+    class Bad(PSMFIter):
+        def _update_coefficient_mean(self, *a):
+            pass
+
+    with pytest.raises(NotImplementedError):
+        Bad(np.zeros((2, 1)), np.zeros((4, 2)), np.eye(2), np.zeros((2, 1)), np.eye(2), {0: np.eye(2)}, {0: np.eye(4)},
+            lambda th, x, t: x)
+
+
+def test_adam_and_learning_rates():
+    from rpsmf_b200 import PSMFIter
+    from rpsmf_b200.learning_rate import ConstantLearningRate, ExponentialLearningRate
+    assert ConstantLearningRate(0.1).get(5) == 0.1
+    assert abs(ExponentialLearningRate(1.0, 0.01, 10).get(10) - 0.01) < 1e-15
+    o = PSMFIter(np.array([[0.5], [0.2]]), np.zeros((4, 2)), np.eye(2), np.zeros((2, 1)), np.eye(2), {0: np.eye(2)},
+                 {0: np.eye(4)}, lambda th, x, t: x)
+    o.adam_init(gam=1e-2)
+    o._gradsum = np.array([[1.0], [-2.0]])
+    o.adam_update(1)
+    # first Adam step moves every coordinate by lr * sign(g) (psmf.py:224-242)
+    assert np.allclose(o._theta[1], np.array([[0.49], [0.21]]), atol=1e-9)
+    o.optim = "sgd"; o.sgd_init(gam=0.1); o.sgd_update(2)
+    assert np.allclose(o._theta[2], np.maximum(o._theta[1] - 0.1 * o._gradsum, 0))
