@@ -180,8 +180,9 @@ def main():
     esize = 8 if args.dtype == "f64" else 4
 
     # rows of this rank (strong scaling at fixed d)
-    rows = [(d * k) // world for k in range(world + 1)]
-    row0, d_loc = rows[rank], rows[rank + 1] - rows[rank]
+    from rpsmf_b200 import shard_rows
+    row0, row1 = shard_rows(d, world, rank)
+    d_loc = row1 - row0
     T = max(args.T // W, 1) * W
     nwin = T // W
     Y, M, C0, x0 = make_device_data(torch, dev, d_loc, row0, d, r, T, dtype)

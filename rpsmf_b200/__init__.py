@@ -14,4 +14,16 @@ from .impute import ProbabilisticSequentialMatrixFactorizer, robust_PSMF  # noqa
 from .psmf import PSMFIter, PSMFIterMissing, PSMFRecursive  # noqa: F401
 from .rpsmf import rPSMFIter, rPSMFIterMissing, rPSMFRecursive  # noqa: F401
 
+
+
+def shard_rows(d, world_size, rank):
+    """Rows [begin, end) of C, y_t, m_t owned by `rank` when one series is sharded over `world_size` GPUs.
+    Shard boundaries fall on 32-row tile boundaries so that every shard keeps the 16-byte alignment the
+    TMA-staged kernel needs."""
+    tiles = (d + 31) // 32
+    b = min(d, ((tiles * rank) // world_size) * 32)
+    e = min(d, ((tiles * (rank + 1)) // world_size) * 32)
+    return b, e
+
+
 __version__ = "0.1.0"

@@ -81,11 +81,19 @@ struct psmf_engine {
     int last_kernel = 0;
     unsigned long long* trace = nullptr;
     int trace_steps = 0;
+    // NVLink mailbox (world_size > 1): [2][MAX_PEERS][nstat_pad] doubles followed by [2][MAX_PEERS] flags
+    void* mbox = nullptr;
+    void* peer_mbox[PSMF_MAX_PEERS] = {nullptr};
+    bool connected = false;
+    unsigned long long step_base = 0;
     cudaStream_t last_stream = nullptr;
     std::string err;
 };
 
 static std::string g_create_error;
+
+static size_t mbox_data_bytes() { return (size_t)2 * PSMF_MAX_PEERS * nstat_pad(MAXR) * sizeof(double); }
+static size_t mbox_bytes() { return mbox_data_bytes() + (size_t)2 * PSMF_MAX_PEERS * sizeof(unsigned long long); }
 
 static int fail(psmf_engine* h, int code, const std::string& msg) {
     if (h)
@@ -112,6 +120,9 @@ static void free_engine(psmf_engine* e) {
     cudaFree(e->partials);
     cudaFree(e->bar);
     cudaFree(e->status);
+    for (int i = 0; i < PSMF_MAX_PEERS; ++i)
+        if (e->peer_mbox[i] && i != e->cfg.rank) cudaIpcCloseMemHandle(e->peer_mbox[i]);
+    cudaFree(e->mbox);
     delete e;
 }
 
@@ -128,7 +139,6 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
         return fail(nullptr, PSMF_E_INVALID, "bad world_size / rank");
     if (cfg->world_size > 1 && cfg->n_series > 1)
         return fail(nullptr, PSMF_E_INVALID, "row sharding (world_size > 1) and batching (n_series > 1) are exclusive");
-    if (cfg->world_size > 1) return fail(nullptr, PSMF_E_INVALID, "world_size > 1: mailbox exchange not built yet");
     const int64_t dg = cfg->d_global > 0 ? cfg->d_global : cfg->d;
     if (dg < cfg->d) return fail(nullptr, PSMF_E_INVALID, "d_global < d");
 
@@ -242,6 +252,10 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     CKC(cudaMalloc(&e->bar, sizeof(unsigned long long)));
     CKC(cudaMalloc(&e->status, sizeof(long long)));
     CKC(cudaMemset(e->status, 0xFF, sizeof(long long)));
+    if (cfg->world_size > 1) {
+        CKC(cudaMalloc(&e->mbox, mbox_bytes()));
+        CKC(cudaMemset(e->mbox, 0, mbox_bytes()));
+    }
 #undef CKC
     *out = e;
     return PSMF_OK;
@@ -339,7 +353,18 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     p.n_series = h->S; p.cps = h->cps;
     p.flags = h->cfg.flags; p.dynamics = h->cfg.dynamics;
     p.alpha = h->cfg.alpha; p.beta = h->cfg.beta;
-    p.world = 1; p.rank = 0;
+    p.world = h->cfg.world_size; p.rank = h->cfg.rank;
+    if (p.world > 1) {
+        if (!h->connected) return fail(h, PSMF_E_STATE, "world_size > 1: call psmf_mailbox_connect before psmf_run");
+        // the mailbox slots are nstat_pad(R) doubles apart (kernel indexing), inside a buffer sized for MAXR
+        p.mbox_local = (double*)h->mbox;
+        p.flag_local = (unsigned long long*)((char*)h->mbox + mbox_data_bytes());
+        for (int i = 0; i < p.world; ++i) {
+            p.mbox_peer[i] = (double*)h->peer_mbox[i];
+            p.flag_peer[i] = (unsigned long long*)((char*)h->peer_mbox[i] + mbox_data_bytes());
+        }
+        p.step_base = h->step_base;
+    }
     p.trace = h->trace; p.trace_steps = h->trace_steps;
     CK(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned long long), st));
     CK(h, cudaMemsetAsync(h->status, 0xFF, sizeof(long long), st));
@@ -363,6 +388,7 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     }
     h->launches_last = 1;
     h->last_stream = st;
+    h->step_base += (unsigned long long)n_steps;
     return PSMF_OK;
 }
 
@@ -402,10 +428,30 @@ extern "C" int psmf_set_trace(psmf_handle h, uint64_t* dev_buf, int32_t steps) {
 }
 
 extern "C" int psmf_mailbox_export(psmf_handle h, void* ipc_handle_64B) {
-    (void)ipc_handle_64B;
-    return fail(h, PSMF_E_INVALID, "mailbox exchange not built yet");
+    if (!h || !ipc_handle_64B) return PSMF_E_INVALID;
+    if (h->cfg.world_size < 2 || !h->mbox) return fail(h, PSMF_E_STATE, "engine was created with world_size == 1");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(h, cudaSetDevice(h->cfg.device));
+    cudaIpcMemHandle_t hd;
+    CK(h, cudaIpcGetMemHandle(&hd, h->mbox));
+    memcpy(ipc_handle_64B, &hd, sizeof(hd));
+    return PSMF_OK;
 }
+
 extern "C" int psmf_mailbox_connect(psmf_handle h, const void* all_ipc_handles, int32_t n) {
-    (void)all_ipc_handles; (void)n;
-    return fail(h, PSMF_E_INVALID, "mailbox exchange not built yet");
+    if (!h || !all_ipc_handles) return PSMF_E_INVALID;
+    if (n != h->cfg.world_size || n < 2) return fail(h, PSMF_E_INVALID, "need one IPC handle per rank");
+    CK(h, cudaSetDevice(h->cfg.device));
+    const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)all_ipc_handles;
+    for (int i = 0; i < n; ++i) {
+        if (i == h->cfg.rank) {
+            h->peer_mbox[i] = h->mbox;
+            continue;
+        }
+        void* ptr = nullptr;
+        CK(h, cudaIpcOpenMemHandle(&ptr, hs[i], cudaIpcMemLazyEnablePeerAccess));
+        h->peer_mbox[i] = ptr;
+    }
+    h->connected = true;
+    return PSMF_OK;
 }

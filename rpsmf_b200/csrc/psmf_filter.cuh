@@ -56,6 +56,22 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 __device__ __forceinline__ void red_release_gpu(unsigned long long* p, unsigned long long v) {
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -452,6 +468,47 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
     if (t + 1 < p.n_steps) predict_cta<R>(p, sh, tid, p.k0 + t + 1, series, nthr);
 }
 
+// ---- cross-GPU exchange of the (already grid-reduced) statistics over NVLink -------------------------------
+// Rows of C are sharded over `world` GPUs; V, P, Q, x, lambda are replicated.  Per step every GPU needs
+// the sum over all shards of nstat(R) doubles (1.2 kB at r = 16).  CTA 0 of each GPU stores its local
+// totals into slot [parity][rank] of every peer's mailbox with plain peer stores (NVLink P2P) and then
+// releases a per-source flag (system scope); every CTA of every GPU polls its LOCAL flags, then adds the
+// world slots in rank order -- the same order on every GPU, so the replicated state stays bit-identical.
+// Two parities make the mailbox safe without a second handshake: a GPU can only be one step ahead of its
+// slowest peer (it needs that peer's flag of the current step to proceed).
+template <int R>
+__device__ __forceinline__ void gpu_exchange(const KParams& p, Smem<R>& sh, int tid, int64_t t, int part, int nthr) {
+    constexpr int NSP = nstat_pad(R), NST = nstat(R);
+    const int parity = (int)((p.step_base + (unsigned long long)t) & 1ULL);
+    const unsigned long long target = p.step_base + (unsigned long long)t + 1ULL;
+    if (part == 0) {
+        if (tid < NST) {
+            const double v = sh.tot[tid];
+            for (int pr = 0; pr < p.world; ++pr)
+                if (pr != p.rank) st_relaxed_sys_f64(p.mbox_peer[pr] + ((size_t)parity * MAX_PEERS + p.rank) * NSP + tid, v);
+        }
+        __threadfence_system();
+        sync_n(nthr);
+        if (tid < p.world && tid != p.rank)
+            st_release_sys(p.flag_peer[tid] + parity * MAX_PEERS + p.rank, target);
+    }
+    if (tid < p.world && tid != p.rank) {
+        const unsigned long long* f = p.flag_local + parity * MAX_PEERS + tid;
+        while (ld_acquire_sys(f) < target) {
+        }
+    }
+    sync_n(nthr);
+    if (tid < NST) {
+        double s = 0.0;
+        for (int src = 0; src < p.world; ++src)
+            s += (src == p.rank) ? sh.tot[tid] : ld_relaxed_sys_f64(p.mbox_local + ((size_t)parity * MAX_PEERS + src) * NSP + tid);
+        sh.part[tid] = s;
+    }
+    sync_n(nthr);
+    if (tid < NST) sh.tot[tid] = sh.part[tid];
+    sync_n(nthr);
+}
+
 // ---- cross-CTA reduction of the statistics, deterministic (fixed summation order) ---------------------
 //   cps <= 16 : every CTA reads all partials after one grid barrier
 //   cps  > 16 : reduce-scatter / all-gather through L2: CTA c sums entries {c, c + cps, ..} over all CTAs
@@ -464,6 +521,7 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, Smem<R>& sh, int t
     if (p.cps == 1) {
         if (tid < NST) sh.tot[tid] = sh.part[tid];
         sync_n(nthr);
+        if (p.world > 1) gpu_exchange<R>(p, sh, tid, t, part, nthr);
         return;
     }
     const int parity = (int)(t & 1);
@@ -510,6 +568,7 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, Smem<R>& sh, int t
         if (tid < NST) sh.tot[tid] = __ldcg(totals + tid);
     }
     sync_n(nthr);
+    if (p.world > 1) gpu_exchange<R>(p, sh, tid, t, part, nthr);
 }
 
 // ---- direct-load persistent kernel: C tiles are read from / written to global memory by the warp that

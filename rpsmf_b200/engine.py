@@ -229,6 +229,23 @@ class FilterEngine:
             done[slot] = ev
         return Xh
 
+    def connect(self, dist):
+        """Row sharding over several GPUs: exchange the CUDA IPC handles of the NVLink mailboxes through the
+        process group `dist` (torch.distributed, any backend) and map every peer's mailbox."""
+        world = dist.get_world_size()
+        buf = (C.c_ubyte * 64)()
+        self._ck(self._L.psmf_mailbox_export(self._h, buf))
+        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+        backend = dist.get_backend()
+        if backend == "nccl":
+            mine = mine.to(self.device)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        blob = b"".join(bytes(g.cpu().tolist()) for g in gathered)
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._ck(self._L.psmf_mailbox_connect(self._h, arr, world))
+        dist.barrier()
+
     def status(self):
         """Synchronise and return the first step with a non-finite N/omega/phi/x, or -1."""
         bad = C.c_int64(-1)
