@@ -240,7 +240,7 @@ def main():
     achieved = bytes_per_launch / mean_launch_s / 1e9
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tr_path):
+    if os.path.exists(tr_path) and world == 1 and d == 1_000_000 and r == 16 and args.dtype == "f64":
         try:
             traffic = json.load(open(tr_path)).get("dram_bytes_per_launch_scaled_to_window", {}).get(str(W))
         except Exception:
