@@ -134,14 +134,26 @@ def algorithmic_bytes_per_filter_step(d_loc, r, esize, masked=True):
 
 
 def cpu_reference_sample(d, r, nsteps, Yh, Mh, C0h, x0h):
-    """Time the oracle port (numpy restatement of the reference step) on the host cores."""
+    """Time the CPU port of the reference step on the host cores: the C/OpenMP restatement
+    (oracle/psmf_oracle_c.c, all host threads) when it is built, else the numpy restatement."""
+    init = init_state(r)
+    from oracle import psmf_oracle_c as pc
+    if pc.available():
+        pc.run(C0h[:1024], x0h, init["P"], init["V"], init["Q"], init["rho"], init["lam"], Yh[:2, :1024], Mh[:2, :1024])
+        Cc = np.ascontiguousarray(C0h, dtype=np.float64)
+        Yc = np.ascontiguousarray(Yh[:nsteps], dtype=np.float64)
+        Mc = np.ascontiguousarray(Mh[:nsteps], dtype=np.uint8)
+        t0 = time.perf_counter()
+        res = pc.run(Cc, x0h, init["P"], init["V"], init["Q"], init["rho"], init["lam"], Yc, Mc, want_X=False)
+        dt = time.perf_counter() - t0
+        assert res["bad"] == -1
+        return nsteps / dt, pc.threads(), "oracle/psmf_oracle_c.c (C/OpenMP O(d r^2) restatement)"
     from oracle import psmf_oracle as po
     try:
         from threadpoolctl import threadpool_info
         threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
         threads = os.cpu_count() or 1
-    init = init_state(r)
     st = po.OracleState(C0h.copy(), x0h.copy(), init["P"], init["V"], init["Q"], init["rho"], init["lam"])
     cfg = po.OracleConfig(robust=True)
     st, _ = po.step(st, cfg, Yh[0], Mh[0].astype(np.float64))          # warm-up step (page faults, BLAS threads)
@@ -149,7 +161,7 @@ def cpu_reference_sample(d, r, nsteps, Yh, Mh, C0h, x0h):
     for t in range(1, nsteps):
         st, _ = po.step(st, cfg, Yh[t], Mh[t].astype(np.float64))
     dt = time.perf_counter() - t0
-    return (nsteps - 1) / dt, threads
+    return (nsteps - 1) / dt, threads, "oracle/psmf_oracle.py (numpy/OpenBLAS O(d r^2) restatement)"
 
 
 def main():
@@ -279,14 +291,13 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        ns = args.cpu_steps or max(4, min(40, int(12e6 / max(d, 1)) * 4))
+        ns = args.cpu_steps or max(8, min(400, int(300e6 / max(d, 1))))     # ~10-20 s of host work at d = 1M
         ns = min(ns, T)
-        dsub = d_loc
-        v, threads = cpu_reference_sample(dsub, r, ns, Y[:ns].double().cpu().numpy(), M[:ns].cpu().numpy(),
-                                          C0.cpu().numpy(), x0.numpy())
-        cpu = dict(value=v * (dsub / d) if world > 1 else v, unit="filter steps/s", cores=threads, kind="port",
-                   sample="%d filter steps of the same workload prefix (d=%d rows, r=%d) through oracle/psmf_oracle.py "
-                          "(numpy/OpenBLAS O(d r^2) restatement; the reference's d x d form cannot run at d=1M)" % (ns - 1, dsub, r))
+        v, threads, what = cpu_reference_sample(d_loc, r, ns, Y[:ns].double().cpu().numpy(), M[:ns].cpu().numpy(),
+                                                C0.cpu().numpy(), x0.numpy())
+        cpu = dict(value=v * (d_loc / d) if world > 1 else v, unit="filter steps/s", cores=threads, kind="port",
+                   sample="%d filter steps of the same workload prefix (d=%d rows, r=%d) through %s; the reference's "
+                          "d x d form cannot run at d=1M" % (ns, d_loc, r, what))
 
     if rank == 0:
         line = dict(
@@ -312,9 +323,9 @@ def run_reference(args):
     d = 1M) on the host cores, same config / metric / unit.  A bench step is a bounded sample of filter steps."""
     from synth import make_problem
     d, r = args.d, args.r
-    est = 0.4 * d / 1e6 + 1e-4                       # seconds per filter step of the numpy port (survey-time figure)
-    per_step = int(max(1, min(8, 60.0 / ((args.steps + args.warmup) * est))))
-    total = per_step * (args.steps + args.warmup) + 1
+    est = 0.05 * d / 1e6 + 1e-4                      # seconds per filter step of the C/OpenMP port (8 threads)
+    per_step = int(max(1, min(40, 40.0 / ((args.steps + args.warmup) * est))))
+    total = per_step                                  # one pool of `per_step` synthetic steps, re-used by every bench step
     rng = np.random.RandomState(20261017)
     Ct = rng.randn(d, r)
     x = rng.randn(r)
@@ -324,26 +335,38 @@ def run_reference(args):
         M[t] = rng.rand(d) >= 0.2
         Y[t] = (Ct @ x + np.sqrt(0.1) * rng.standard_t(3, d)) * M[t]
     C0 = rng.rand(d, r); x0 = rng.rand(r)
-    from oracle import psmf_oracle as po
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
     init = init_state(r)
-    st = po.OracleState(C0, x0, init["P"], init["V"], init["Q"], init["rho"], init["lam"])
-    cfg = po.OracleConfig(robust=True)
-    t_idx = 0
+    from oracle import psmf_oracle_c as pc
+    if pc.available():
+        threads = pc.threads()
+        what = "oracle/psmf_oracle_c.c (C/OpenMP port, %d threads)" % threads
+        st = dict(C=C0, x=x0, P=init["P"], V=init["V"], Q=init["Q"], rho=init["rho"], lam=init["lam"])
+
+        def advance(a, b):
+            res = pc.run(st["C"], st["x"], st["P"], st["V"], st["Q"], st["rho"], st["lam"], Y[a:b], M[a:b], want_X=False)
+            st.update({k: res[k] for k in ("C", "x", "P", "V", "Q", "rho", "lam")})
+    else:
+        from oracle import psmf_oracle as po
+        try:
+            from threadpoolctl import threadpool_info
+            threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        except Exception:
+            threads = os.cpu_count() or 1
+        what = "oracle/psmf_oracle.py (numpy/OpenBLAS port)"
+        box = [po.OracleState(C0, x0, init["P"], init["V"], init["Q"], init["rho"], init["lam"])]
+        cfg = po.OracleConfig(robust=True)
+
+        def advance(a, b):
+            for t in range(a, b):
+                box[0], _ = po.step(box[0], cfg, Y[t], M[t].astype(np.float64))
     for _ in range(args.warmup):
-        for _ in range(per_step):
-            st, _ = po.step(st, cfg, Y[t_idx], M[t_idx].astype(np.float64)); t_idx += 1
+        advance(0, per_step)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        for _ in range(per_step):
-            st, _ = po.step(st, cfg, Y[t_idx], M[t_idx].astype(np.float64)); t_idx += 1
+        advance(0, per_step)
     dt = time.perf_counter() - t0
     v = args.steps * per_step / dt
-    sample = "%d filter steps per bench step, d=%d r=%d, oracle/psmf_oracle.py (numpy/OpenBLAS port)" % (per_step, d, r)
+    sample = "%d filter steps per bench step, d=%d r=%d, %s" % (per_step, d, r, what)
     line = dict(impl="reference", metric="PSMF filter steps/sec at d=1M,r=16", value=v, unit="filter steps/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt / args.steps * 1e3,
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",

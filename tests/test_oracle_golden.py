@@ -155,3 +155,22 @@ def test_theta_gradient_closed_form(tag, robust):
         gs += po.theta_grad_cos(robust, theta, st.x, k, Y[k - 1], st.C, st.V, eta, st.lam, d)
         st, _ = po.step(st, cfg, Y[k - 1], None, k=k)
     assert relerr(gs, g[tag + "_grads"][0]) < 1e-6
+
+
+@pytest.mark.parametrize("robust", [True, False])
+def test_c_oracle_matches_numpy_oracle(robust):
+    """oracle/psmf_oracle_c.c (multi-threaded CPU baseline of bench.py) against the pinned numpy oracle."""
+    from oracle import psmf_oracle_c as pc
+    if not pc.available():
+        pytest.skip("oracle/libpsmf_oracle.so not built (python -c 'import __graft_entry__ as g; g.build()')")
+    from synth import impute_init, make_problem
+    d, r, T = 5000, 16, 30
+    Y, M, C0, x0 = make_problem(d, r, T, seed=99)
+    init = impute_init(r)
+    res = pc.run(C0, x0, init["P"], init["V"], init["Q"], init["rho"], init["lam"], Y, M, robust=robust, cupdate_vt=robust)
+    st = po.OracleState(C0.copy(), x0.copy(), init["P"], init["V"], init["Q"], init["rho"], init["lam"])
+    st, X, _, _ = po.run(st, po.OracleConfig(robust=robust, c_update_transpose=robust), Y, M.astype(float))
+    assert res["bad"] == -1
+    assert relerr(res["X"], X) < TOL and relerr(res["C"], st.C) < TOL
+    assert relerr(res["P"], st.P) < TOL and relerr(res["V"], st.V) < TOL
+    assert relerr(res["rho"], st.rho) < TOL and relerr(res["lam"], st.lam) < TOL
