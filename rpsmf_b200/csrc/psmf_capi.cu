@@ -92,7 +92,7 @@ struct psmf_engine {
 
 static std::string g_create_error;
 
-static size_t mbox_data_bytes() { return (size_t)2 * PSMF_MAX_PEERS * nstat_pad(MAXR) * sizeof(double); }
+static size_t mbox_data_bytes() { return (size_t)2 * PSMF_MAX_PEERS * 192 * sizeof(double); }   // slots of <= nstat2_pad(16) = 176 doubles
 static size_t mbox_bytes() { return mbox_data_bytes() + (size_t)2 * PSMF_MAX_PEERS * sizeof(unsigned long long); }
 
 static int fail(psmf_engine* h, int code, const std::string& msg) {
@@ -194,7 +194,8 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     if (cfg->kernel != 1 && e->d % 16 == 0) {
         const int TS = V2_TS;
         auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
-        const size_t slot = r128((size_t)TS * e->R * TILE * e->esize) + r128((size_t)TS * TILE * e->esize) + r128((size_t)TS * TILE);
+        // slot = C chunk + two time steps of y and m (software pipeline, psmf_stream.cuh SlotLayout)
+        const size_t slot = r128((size_t)TS * e->R * TILE * e->esize) + 2 * r128((size_t)TS * TILE * e->esize) + 2 * r128((size_t)TS * TILE);
         int cps2;
         if (e->S > 1) cps2 = 1;
         else if (cfg->ctas > 0) cps2 = cfg->ctas;
@@ -230,7 +231,7 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     }
 
     const size_t cbytes = (size_t)e->S * e->ntiles * TILE * e->R * e->esize;
-    const int nsp = nstat_pad(e->R);
+    const int nsp = (ngram(e->R) + 2 * e->R + 5 + 7) / 8 * 8;      // >= nstat_pad(R): pipelined statistics (nstat2_pad)
 #define CKC(call)                                                                                            \
     do {                                                                                                     \
         cudaError_t e__ = (call);                                                                            \

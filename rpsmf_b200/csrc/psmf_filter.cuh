@@ -476,14 +476,14 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
 // world slots in rank order -- the same order on every GPU, so the replicated state stays bit-identical.
 // Two parities make the mailbox safe without a second handshake: a GPU can only be one step ahead of its
 // slowest peer (it needs that peer's flag of the current step to proceed).
-template <int R>
-__device__ __forceinline__ void gpu_exchange(const KParams& p, Smem<R>& sh, int tid, int64_t t, int part, int nthr) {
-    constexpr int NSP = nstat_pad(R), NST = nstat(R);
+template <int NST, int NSP>
+__device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restrict__ tot, double* __restrict__ tmp, int tid,
+                                             int64_t t, int part, int nthr) {
     const int parity = (int)((p.step_base + (unsigned long long)t) & 1ULL);
     const unsigned long long target = p.step_base + (unsigned long long)t + 1ULL;
     if (part == 0) {
         if (tid < NST) {
-            const double v = sh.tot[tid];
+            const double v = tot[tid];
             for (int pr = 0; pr < p.world; ++pr)
                 if (pr != p.rank) st_relaxed_sys_f64(p.mbox_peer[pr] + ((size_t)parity * MAX_PEERS + p.rank) * NSP + tid, v);
         }
@@ -501,11 +501,11 @@ __device__ __forceinline__ void gpu_exchange(const KParams& p, Smem<R>& sh, int 
     if (tid < NST) {
         double s = 0.0;
         for (int src = 0; src < p.world; ++src)
-            s += (src == p.rank) ? sh.tot[tid] : ld_relaxed_sys_f64(p.mbox_local + ((size_t)parity * MAX_PEERS + src) * NSP + tid);
-        sh.part[tid] = s;
+            s += (src == p.rank) ? tot[tid] : ld_relaxed_sys_f64(p.mbox_local + ((size_t)parity * MAX_PEERS + src) * NSP + tid);
+        tmp[tid] = s;
     }
     sync_n(nthr);
-    if (tid < NST) sh.tot[tid] = sh.part[tid];
+    if (tid < NST) tot[tid] = tmp[tid];
     sync_n(nthr);
 }
 
@@ -514,21 +514,20 @@ __device__ __forceinline__ void gpu_exchange(const KParams& p, Smem<R>& sh, int 
 //   cps  > 16 : reduce-scatter / all-gather through L2: CTA c sums entries {c, c + cps, ..} over all CTAs
 //               (coalesced reads of a transposed partial array), a second barrier publishes the totals.
 // sh.part -> sh.tot; ends with a barrier over the `nthr` threads.
-template <int R>
-__device__ __forceinline__ void grid_reduce(const KParams& p, Smem<R>& sh, int tid, int lane, int warp, int64_t t,
-                                            int series, int part, int nthr) {
-    constexpr int NSP = nstat_pad(R), NST = nstat(R);
+template <int NST, int NSP>
+__device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict__ part_v, double* __restrict__ tot, int tid,
+                                            int lane, int warp, int64_t t, int series, int part, int nthr) {
     if (p.cps == 1) {
-        if (tid < NST) sh.tot[tid] = sh.part[tid];
+        if (tid < NST) tot[tid] = part_v[tid];
         sync_n(nthr);
-        if (p.world > 1) gpu_exchange<R>(p, sh, tid, t, part, nthr);
+        if (p.world > 1) gpu_exchange<NST, NSP>(p, tot, part_v, tid, t, part, nthr);
         return;
     }
     const int parity = (int)(t & 1);
     const int cps = p.cps;
     if (cps <= 16) {
         double* mine = p.partials + ((size_t)parity * cps + part) * NSP;
-        if (tid < NST) mine[tid] = sh.part[tid];
+        if (tid < NST) mine[tid] = part_v[tid];
         stamp(p, t, 3);
         grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), nthr);
         stamp(p, t, 4);
@@ -537,14 +536,14 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, Smem<R>& sh, int t
             double v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = c < cps ? __ldcg(basep + (size_t)c * NSP + tid) : 0.0;
-            sh.tot[tid] = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) +
+            tot[tid] = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) +
                           (((v[8] + v[9]) + (v[10] + v[11])) + ((v[12] + v[13]) + (v[14] + v[15])));
         }
     } else {
         const int pstr = (cps + 7) & ~7;
         double* pT = p.partials + (size_t)parity * NSP * (pstr + 1);
         double* totals = pT + (size_t)NSP * pstr;
-        if (tid < NST) pT[(size_t)tid * pstr + part] = sh.part[tid];
+        if (tid < NST) pT[(size_t)tid * pstr + part] = part_v[tid];
         stamp(p, t, 3);
         grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 1), nthr);
         const int nw = nthr >> 5;
@@ -565,10 +564,10 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, Smem<R>& sh, int t
         }
         grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 2), nthr);
         stamp(p, t, 4);
-        if (tid < NST) sh.tot[tid] = __ldcg(totals + tid);
+        if (tid < NST) tot[tid] = __ldcg(totals + tid);
     }
     sync_n(nthr);
-    if (p.world > 1) gpu_exchange<R>(p, sh, tid, t, part, nthr);
+    if (p.world > 1) gpu_exchange<NST, NSP>(p, tot, part_v, tid, t, part, nthr);
 }
 
 // ---- direct-load persistent kernel: C tiles are read from / written to global memory by the warp that
@@ -656,7 +655,7 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
             for (int w = 0; w < NW; ++w) s += sh.red[w * NSP + tid];
             sh.part[tid] = s;
         }
-        grid_reduce<R>(p, sh, tid, lane, warp, t, series, part, blockDim.x);
+        grid_reduce<NST, NSP>(p, sh.part, sh.tot, tid, lane, warp, t, series, part, blockDim.x);
         stamp(p, t, 5);
         small_update<R>(p, sh, tid, lane, warp, series, t, writer, blockDim.x);
         stamp(p, t, 6);

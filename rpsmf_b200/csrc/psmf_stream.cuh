@@ -1,18 +1,30 @@
-// TMA-staged PSMF / rPSMF filter kernel (sm_100a): the large-d path.
+// TMA-staged, software-pipelined PSMF / rPSMF filter kernel (sm_100a): the large-d path.
 //
-// Same step as psmf_filter.cuh, but C never travels through registers from global memory.  A producer
-// warp moves contiguous CHUNKS of the tiled C (plus the matching slices of y_t and m_t) between HBM and a
-// ring of shared-memory slots with bulk asynchronous copies (cp.async.bulk, the 1-D TMA path: UBLKCP in
-// SASS) that complete on mbarriers; the consumer warps read tiles from shared memory, apply the pending
-// rank-1 update, accumulate the statistics, write the updated tile back into the slot, and the producer
-// bulk-stores it to HBM.  Two regimes, chosen per CTA:
+// Three warp groups per CTA (one CTA per SM, cooperative launch):
 //
-//   streaming  (chunks of the CTA > slots): the slots form a ring; per step every chunk is loaded once and
-//              stored once -> HBM traffic = 2 d r s_C + d (s_y + 1) bytes per step.  While the consumers
-//              sit in the reduction / grid barrier / r x r solve, the producer already fills the ring
-//              with the first chunks of the next step.
-//   resident   (chunks <= slots): C is loaded once, stays in shared memory for the whole launch and is
-//              stored once at the end; only y_t / m_t stream.
+//   producer (1 warp, one thread)  moves contiguous CHUNKS of the tiled C (plus the matching slices of y and
+//       m) between HBM and a ring of shared-memory slots with bulk asynchronous copies (cp.async.bulk, the
+//       1-D TMA path: UBLKCP in SASS) that complete on mbarriers, and bulk-stores updated chunks back.
+//       streaming (chunks of the CTA > slots): ring, every chunk loaded and stored once per step;
+//       resident  (chunks <= slots): C is loaded once, stays in shared memory for the whole launch.
+//   pass warps (9)   one warp per 32-row tile, all warps independent (psmf_filter.cuh: lane = row for the
+//       rank-1 update / y_hat / e, fp64 DMMA fragments for the Gram-type sums).
+//   control warps (6) CTA partial -> deterministic grid reduction (+ NVLink exchange) -> r x r solve.
+//
+// Software pipeline.  The statistics of step t are sums over C_t = C_{t-1} + e_{t-1} g_{t-1}', and g_{t-1}
+// only exists after the solve of step t-1.  Expanding the rank-1 term,
+//
+//     A_t  = sum m_t c c' = A0 + u g' + g u' + kappa g g'        A0 = sum m_t c c',  u = sum m_t e c
+//     h_t  = sum m_t y_t c = h0 + psi g                          h0 = sum m_t y_t c, psi = sum m_t y_t e
+//     bu_t = sum m_t e_t c = h_t - A_t xbar_t                     (e_t = y_t - m_t c.xbar_t)
+//     q1_t = sum m_t e_t^2 = gamma - 2 xbar_t' h_t + xbar_t' A_t xbar_t,   gamma = sum m_t y_t^2
+//
+// with c = rows of C_{t-1}, e = e_{t-1}, g = g_{t-1}: every sum on the right is independent of the solve of
+// step t-1.  So pass P_t (which turns C_{t-2} in HBM into C_{t-1}, computes e_{t-1} and the sums for step t)
+// only needs the solve of step t-2 and runs CONCURRENTLY with the reduction / solve of step t-1; the solve of
+// step t assembles A_t, bu_t, q1_t from the reduced sums in O(r^2) and proceeds as in psmf_filter.cuh.  The
+// step time becomes max(pass, (pass + reduce + solve) / 2) instead of pass + reduce + solve.  One extra
+// read of y_t / m_t per step (+3 % HBM bytes) pays for it; C is still read and written once per step.
 //
 // Requirements checked by the host (else the direct-load kernel of psmf_filter.cuh is used): 16-byte
 // aligned Y / M base pointers and time strides, d a multiple of 16.
@@ -22,8 +34,14 @@
 namespace psmf {
 
 constexpr int MAXSLOT = 64;
+constexpr int V2_CTRL_WARPS = 6;                                   // = GJ_THREADS / 32
+constexpr int V2_PASS_WARPS = V2_CWARPS - V2_CTRL_WARPS;           // 9
+static_assert(V2_CTRL_WARPS * 32 == GJ_THREADS, "control warps run the Gauss-Jordan");
 
 __host__ __device__ constexpr int s_threads() { return (V2_CWARPS + 1) * 32; }
+// pipelined statistics: packed upper triangle of A0, u (R), h0 (R), kappa, psi, gamma, q0, n_obs
+__host__ __device__ constexpr int nstat2(int R) { return ngram(R) + 2 * R + 5; }
+__host__ __device__ constexpr int nstat2_pad(int R) { return (nstat2(R) + 7) / 8 * 8; }
 
 __host__ __device__ constexpr size_t round128(size_t x) { return (x + 127) / 128 * 128; }
 template <int R, typename T>
@@ -31,9 +49,11 @@ struct SlotLayout {
     static constexpr int TS = V2_TS;
     static constexpr size_t TILE_BYTES = (size_t)R * TILE * sizeof(T);
     static constexpr size_t CB = round128(TS * TILE_BYTES);
-    static constexpr size_t YB = round128((size_t)TS * TILE * sizeof(T));
-    static constexpr size_t MB = round128((size_t)TS * TILE);
-    static constexpr size_t SLOT = CB + YB + MB;
+    static constexpr size_t YB1 = round128((size_t)TS * TILE * sizeof(T));   // one time step of y for the chunk
+    static constexpr size_t MB1 = round128((size_t)TS * TILE);               // one time step of m
+    static constexpr size_t YOFF = CB;                                       // y region of parity b at YOFF + b*YB1
+    static constexpr size_t MOFF = CB + 2 * YB1;
+    static constexpr size_t SLOT = CB + 2 * YB1 + 2 * MB1;
 };
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------------
@@ -89,87 +109,199 @@ __device__ __forceinline__ void bulk_wait() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- consumer: one warp over its tiles of one pass (tile tl of the CTA belongs to warp tl % V2_CWARPS) ----
-// FLUSH: apply the pending rank-1 update only (the pass after the last step).
+// shared state of the pipeline (in addition to Smem<R>)
+template <int R>
+struct PipeSmem {
+    static constexpr int NSP2 = nstat2_pad(R);
+    double tot2[NSP2];
+    double part2[NSP2];
+    double par[2][2 * R];          // par[t & 1] = {g_t (R), xbar_{t+1} (R)} published by the solve of step t
+    double xb0[R];                 // xbar_0 (from the state entering the launch)
+    uint64_t full[MAXSLOT];        // slot loaded            (producer -> pass warps)
+    uint64_t done[MAXSLOT];        // slot processed         (pass warps -> producer)
+    uint64_t stats_full[2];        // partial sums of pass t written        (pass warps -> control)
+    uint64_t red_free;             // partial sums consumed                  (control -> pass warps)
+    uint64_t par_full[2];          // par[t & 1] published                   (control -> pass warps)
+};
+
+// per-warp accumulators of one pipelined pass
+struct PassAcc {
+    double g00[2], g01[2], g11[2];   // fragments of A0 = sum m_t c c'
+    double u0[2], u1[2];             // fragments of [u | h0] for columns 0..7 / 8..15 of C
+    double v[5];                     // per-lane: kappa, psi, gamma, q0, n_obs
+    __device__ __forceinline__ void zero() {
+        g00[0] = g00[1] = g01[0] = g01[1] = g11[0] = g11[1] = u0[0] = u0[1] = u1[0] = u1[1] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[i] = 0.0;
+    }
+};
+
+// ---- pass warp: pass `pass` over the tiles tl = wp, wp + NPW, ... of the CTA ---------------------------
+//   pass p in [0, n):  C_{p-2} -> C_{p-1} in the slot, e_{p-1} -> ebuf, Yrec_{p-1}, sums for step p
+//   pass n (FLUSH):    C_{n-2} -> C_n (both pending rank-1 updates), Yrec_{n-1}
 template <int R, typename T, bool FLUSH>
-__device__ __forceinline__ void s_warp_pass(const KParams& p, Smem<R>& sh, double* __restrict__ ebuf,
-                                            unsigned char* __restrict__ slots, uint64_t* full, uint64_t* done,
-                                            T* __restrict__ Yrec_t, bool masked, int tb, int nt, int nslot, int64_t pass,
-                                            int warp, int lane) {
+__device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, double* __restrict__ ebuf,
+                                            unsigned char* __restrict__ slots, double* __restrict__ red, T* __restrict__ Yrec_prev,
+                                            bool masked, int tb, int nt, int nslot, int64_t pass, int wp, int lane) {
     using L = SlotLayout<R, T>;
-    constexpr int NSP = nstat_pad(R), TS = L::TS;
-    const double w1 = sh.w1, w0 = sh.w0;
+    constexpr int TS = L::TS, NSP2 = nstat2_pad(R);
     const int nchunks = (nt + TS - 1) / TS;
     const bool streaming = nchunks > nslot;
-    TileAcc<R> acc;
+    // g_{pass-2} and xbar_{pass-1} were published by the solve of step pass-2
+    const double* gp = (pass >= 2) ? ps.par[(pass - 2) & 1] : ps.xb0;
+    const double* xbp = (pass >= 2) ? ps.par[(pass - 2) & 1] + R : ps.xb0;
+    const double* gl = ps.par[(pass - 1) & 1];                          // g_{n-1} (flush only)
+    const int ycur = (int)(pass & 1), yprev = ycur ^ 1;
+    PassAcc acc;
     acc.zero();
 
-    for (int tl = warp; tl < nt; tl += V2_CWARPS) {
+    for (int tl = wp; tl < nt; tl += V2_PASS_WARPS) {
         const int k = tl / TS, i = tl - k * TS;
         const int64_t kk = pass * nchunks + k;
         const int slot = streaming ? (int)(kk % nslot) : k;
         const uint32_t parity = (uint32_t)((streaming ? kk / nslot : pass) & 1);
         unsigned char* sb = slots + (size_t)slot * L::SLOT;
-        mbar_wait(&full[slot], parity);
+        mbar_wait(&ps.full[slot], parity);
         const int64_t row = (int64_t)(tb + tl) * TILE + lane;
         const int rl = tl * TILE + lane;
+        const bool inb = row < p.d;
         T* tile = reinterpret_cast<T*>(sb) + (size_t)i * (R * TILE);
-        const double ep = ebuf[rl];
-        if constexpr (FLUSH) {
+        const T* yp_s = reinterpret_cast<const T*>(sb + L::YOFF + yprev * L::YB1) + i * TILE;
+        const T* yc_s = reinterpret_cast<const T*>(sb + L::YOFF + ycur * L::YB1) + i * TILE;
+        const unsigned char* mp_s = sb + L::MOFF + yprev * L::MB1 + i * TILE;
+        const unsigned char* mc_s = sb + L::MOFF + ycur * L::MB1 + i * TILE;
+
+        // ---- phase 1, lane = row ----
+        double c[R];
 #pragma unroll
-            for (int j = 0; j < R; ++j) tile[tile_pos(j, lane)] = (T)fma(ep, sh.g[j], (double)tile[tile_pos(j, lane)]);
+        for (int j = 0; j < R; ++j) c[j] = (double)tile[tile_pos(j, lane)];
+        double e = 0.0;
+        if (pass >= 2) {                                           // C_{p-1} = C_{p-2} + e_{p-2} g_{p-2}'   (rPSMF.py:111)
+            const double epp = ebuf[rl];
+#pragma unroll
+            for (int j = 0; j < R; ++j) c[j] = fma(epp, gp[j], c[j]);
+        }
+        if (pass >= 1) {                                           // e_{p-1} = y_{p-1} - m_{p-1} C_{p-1} xbar_{p-1}
+            double yh4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < R; ++j) yh4[j & 3] = fma(c[j], xbp[j], yh4[j & 3]);     // rPSMF.py:89
+            const double yh = (yh4[0] + yh4[1]) + (yh4[2] + yh4[3]);
+            bool mprev = inb;
+            if (masked && inb) mprev = mp_s[lane] != 0;
+            const double yprv = inb ? (double)yp_s[lane] : 0.0;
+            e = yprv - (mprev ? yh : 0.0);                         // rPSMF.py:101
+            if (Yrec_prev != nullptr && inb) Yrec_prev[row] = (T)yh;
+        }
+        if constexpr (FLUSH) {                                     // C_n = C_{n-1} + e_{n-1} g_{n-1}'
+#pragma unroll
+            for (int j = 0; j < R; ++j) c[j] = fma(e, gl[j], c[j]);
+#pragma unroll
+            for (int j = 0; j < R; ++j) tile[tile_pos(j, lane)] = (T)c[j];
         } else {
-            double c[R];
-#pragma unroll
-            for (int j = 0; j < R; ++j) c[j] = (double)tile[tile_pos(j, lane)];
-            const bool inb = row < p.d;
-            bool mi = inb;
-            if (masked && inb) mi = (sb + L::CB + L::YB)[i * TILE + lane] != 0;
-            const double yi = inb ? (double)reinterpret_cast<const T*>(sb + L::CB)[i * TILE + lane] : 0.0;
-            double e, yh;
-            row_stats<R>(acc, sh, c, ep, inb, mi, yi, w1, w0, e, yh);
 #pragma unroll
             for (int j = 0; j < R; ++j) tile[tile_pos(j, lane)] = (T)c[j];
             ebuf[rl] = e;
-            if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
+            bool mi = inb;
+            if (masked && inb) mi = mc_s[lane] != 0;
+            const double yi = inb ? (double)yc_s[lane] : 0.0;
+            acc.v[0] += mi ? e * e : 0.0;                          // kappa
+            acc.v[1] += mi ? yi * e : 0.0;                         // psi
+            acc.v[2] += mi ? yi * yi : 0.0;                        // gamma
+            acc.v[3] += mi ? 0.0 : yi * yi;                        // q0 (rows missing at step p: e_p = y_p)
+            acc.v[4] += mi ? 1.0 : 0.0;                            // n_obs
             const unsigned mbits = __ballot_sync(FULL, mi);
             __syncwarp();
-            tile_gram<R, T>(acc, tile, mbits, lane);
+            // ---- phase 2: A0 += sum m c c', [u | h0] += sum m c [e, y]  (fp64 DMMA, k = row) ----
+            const int kq = lane & 3, mm = lane >> 2;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const int r4 = 4 * s + kq;
+                const bool mrow = (mbits >> r4) & 1u;
+                const int pos = r4 ^ (mm << 2);
+                const double a0 = (mm < R) ? (double)tile[mm * 32 + pos] : 0.0;
+                const double b0 = mrow ? a0 : 0.0;
+                double bx = 0.0;                                   // B columns 0 / 1 = m e_{p-1} / m y_p
+                if (mm == 0) bx = mrow ? ebuf[tl * TILE + r4] : 0.0;
+                if (mm == 1) bx = (mrow && (int64_t)(tb + tl) * TILE + r4 < p.d) ? (double)yc_s[r4] : 0.0;
+                dmma884(acc.g00, a0, b0);
+                dmma884(acc.u0, a0, bx);
+                if constexpr (R > 8) {
+                    const double a1 = (8 + mm < R) ? (double)tile[(8 + mm) * 32 + pos] : 0.0;
+                    const double b1 = mrow ? a1 : 0.0;
+                    dmma884(acc.g01, a0, b1);
+                    dmma884(acc.g11, a1, b1);
+                    dmma884(acc.u1, a1, bx);
+                }
+            }
         }
         // this warp is done with its tile: make the generic-proxy writes visible to the bulk store and
-        // release the slot (the warp that owns the last tile of a partial chunk also signs for the
-        // tiles that do not exist)
+        // release the slot (the owner of the last tile of a partial chunk also signs for the missing tiles)
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
             const int ntc = min(TS, nt - k * TS);
-            mbar_arrive_n(&done[slot], (i == ntc - 1) ? (uint32_t)(TS - ntc + 1) : 1u);
+            mbar_arrive_n(&ps.done[slot], (i == ntc - 1) ? (uint32_t)(TS - ntc + 1) : 1u);
         }
     }
-    if constexpr (!FLUSH) acc_writeout<R>(acc, sh.red + warp * NSP, w1, lane);
+    if constexpr (!FLUSH) {
+        // the control warps have consumed the partial sums of the previous pass
+        if (pass >= 1) mbar_wait(&ps.red_free, (uint32_t)((pass - 1) & 1));
+        double* r0 = red + wp * NSP2;
+        const int kq = lane & 3, mm = lane >> 2;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            const int n = 2 * kq + x;
+            if (mm <= n && n < R) r0[gram_off(R, mm) + (n - mm)] = acc.g00[x];
+            if constexpr (R > 8) {
+                if (8 + n < R) r0[gram_off(R, mm) + (8 + n - mm)] = acc.g01[x];
+                if (mm <= n && 8 + n < R) r0[gram_off(R, 8 + mm) + (n - mm)] = acc.g11[x];
+            }
+        }
+        if (kq == 0) {                                             // D[mm][0] = u_mm, D[mm][1] = h0_mm
+            if (mm < R) {
+                r0[ngram(R) + mm] = acc.u0[0];
+                r0[ngram(R) + R + mm] = acc.u0[1];
+            }
+            if constexpr (R > 8) {
+                if (8 + mm < R) {
+                    r0[ngram(R) + 8 + mm] = acc.u1[0];
+                    r0[ngram(R) + R + 8 + mm] = acc.u1[1];
+                }
+            }
+        }
+        int base = 0, lim = 5;
+        bfly<5, 16, 5>(acc.v, lane, base, lim);
+        if (base < lim) r0[ngram(R) + 2 * R + base] = acc.v[0];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ps.stats_full[pass & 1]);
+    }
 }
 
 // ---- producer: one thread drives all bulk copies of the CTA -------------------------------------------
 template <int R, typename T>
-__device__ void s_producer(const KParams& p, unsigned char* slots, uint64_t* full, uint64_t* done, T* Cs, int series,
-                           int tb, int nt, int nslot) {
+__device__ void s_producer(const KParams& p, PipeSmem<R>& ps, unsigned char* slots, T* Cs, int series, int tb, int nt,
+                           int nslot) {
     using L = SlotLayout<R, T>;
     constexpr int TS = L::TS;
     const int nchunks = (nt + TS - 1) / TS;
     const bool streaming = nchunks > nslot;
     const int64_t npass = p.n_steps + 1;
     const bool masked = p.M != nullptr;
+    const T* Yb = reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst;
+    const uint8_t* Mb = masked ? p.M + (int64_t)series * p.msst : nullptr;
     int64_t kk = 0;
     for (int64_t pass = 0; pass < npass; ++pass) {
         const bool last = pass == p.n_steps;
-        const T* Yt = last ? nullptr : reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst + pass * p.ldy;
-        const uint8_t* Mt = (last || !masked) ? nullptr : p.M + (int64_t)series * p.msst + pass * p.ldm;
+        // y/m of the current step go to region (pass & 1); the other region already holds y_{pass-1} in the
+        // resident regime (slots persist) and is reloaded in the streaming regime
+        const bool load_cur = !last;
+        const bool load_prev = streaming && pass >= 1;
         for (int k = 0; k < nchunks; ++k, ++kk) {
             const int slot = streaming ? (int)(kk % nslot) : k;
             const int64_t use = streaming ? kk / nslot : pass;
             unsigned char* sb = slots + (size_t)slot * L::SLOT;
             if (use > 0) {
-                mbar_wait(&done[slot], (uint32_t)((use - 1) & 1));        // consumers released the previous occupant
+                mbar_wait(&ps.done[slot], (uint32_t)((use - 1) & 1));     // pass warps released the previous occupant
                 if (streaming) {
                     const int pk = (int)((kk - nslot) % nchunks);
                     const int ptiles = min(TS, nt - pk * TS);
@@ -187,16 +319,24 @@ __device__ void s_producer(const KParams& p, unsigned char* slots, uint64_t* ful
             vrows = vrows < 0 ? 0 : (vrows > (int64_t)ntc * TILE ? (int64_t)ntc * TILE : vrows);
             const bool loadC = streaming || pass == 0;
             const uint32_t cbytes = loadC ? (uint32_t)(ntc * L::TILE_BYTES) : 0u;
-            const uint32_t ybytes = (Yt != nullptr) ? (uint32_t)(vrows * sizeof(T)) : 0u;
-            const uint32_t mbytes = (Mt != nullptr) ? (uint32_t)vrows : 0u;
-            const uint32_t tx = cbytes + ybytes + mbytes;
+            const uint32_t ybytes = (uint32_t)(vrows * sizeof(T));
+            const uint32_t mbytes = masked ? (uint32_t)vrows : 0u;
+            const uint32_t tx = cbytes + (load_cur ? ybytes + mbytes : 0u) + (load_prev ? ybytes + mbytes : 0u);
             if (tx == 0) {
-                mbar_arrive(&full[slot]);
+                mbar_arrive(&ps.full[slot]);
             } else {
-                mbar_arrive_expect_tx(&full[slot], tx);
-                if (cbytes) bulk_load(sb, Cs + (size_t)(tb + k * TS) * (R * TILE), cbytes, &full[slot]);
-                if (ybytes) bulk_load(sb + L::CB, Yt + row0, ybytes, &full[slot]);
-                if (mbytes) bulk_load(sb + L::CB + L::YB, Mt + row0, mbytes, &full[slot]);
+                mbar_arrive_expect_tx(&ps.full[slot], tx);
+                if (cbytes) bulk_load(sb, Cs + (size_t)(tb + k * TS) * (R * TILE), cbytes, &ps.full[slot]);
+                if (load_cur && ybytes) {
+                    const int b = (int)(pass & 1);
+                    bulk_load(sb + L::YOFF + b * L::YB1, Yb + pass * p.ldy + row0, ybytes, &ps.full[slot]);
+                    if (mbytes) bulk_load(sb + L::MOFF + b * L::MB1, Mb + pass * p.ldm + row0, mbytes, &ps.full[slot]);
+                }
+                if (load_prev && ybytes) {
+                    const int b = (int)((pass - 1) & 1);
+                    bulk_load(sb + L::YOFF + b * L::YB1, Yb + (pass - 1) * p.ldy + row0, ybytes, &ps.full[slot]);
+                    if (mbytes) bulk_load(sb + L::MOFF + b * L::MB1, Mb + (pass - 1) * p.ldm + row0, mbytes, &ps.full[slot]);
+                }
             }
         }
     }
@@ -204,7 +344,7 @@ __device__ void s_producer(const KParams& p, unsigned char* slots, uint64_t* ful
     if (streaming) {
         for (int64_t j = kk - nslot; j < kk; ++j) {
             const int slot = (int)(j % nslot);
-            mbar_wait(&done[slot], (uint32_t)((j / nslot) & 1));
+            mbar_wait(&ps.done[slot], (uint32_t)((j / nslot) & 1));
             const int pk = (int)(j % nchunks);
             const int ptiles = min(TS, nt - pk * TS);
             bulk_store(Cs + (size_t)(tb + pk * TS) * (R * TILE), slots + (size_t)slot * L::SLOT, (uint32_t)(ptiles * L::TILE_BYTES));
@@ -212,7 +352,7 @@ __device__ void s_producer(const KParams& p, unsigned char* slots, uint64_t* ful
         }
     } else {
         for (int k = 0; k < nchunks; ++k) {
-            mbar_wait(&done[k], (uint32_t)((npass - 1) & 1));
+            mbar_wait(&ps.done[k], (uint32_t)((npass - 1) & 1));
             const int ptiles = min(TS, nt - k * TS);
             bulk_store(Cs + (size_t)(tb + k * TS) * (R * TILE), slots + (size_t)k * L::SLOT, (uint32_t)(ptiles * L::TILE_BYTES));
             bulk_commit();
@@ -221,15 +361,74 @@ __device__ void s_producer(const KParams& p, unsigned char* slots, uint64_t* ful
     bulk_wait<0>();
 }
 
+// ---- control warps: pipelined sums of step t (+ g_{t-1}, xbar_t) -> statistics vector of psmf_filter.cuh ----
+// sh.g = g_{t-1}, sh.xb = xbar_t, sh.w1/w0 for step t are current (left by the solve of step t-1).
+template <int R>
+__device__ __forceinline__ void assemble_stats(Smem<R>& sh, PipeSmem<R>& ps, int tid, int nthr) {
+    constexpr int NGm = ngram(R);
+    const double* t2 = ps.tot2;
+    const double kappa = t2[NGm + 2 * R + 0], psi = t2[NGm + 2 * R + 1], gamma = t2[NGm + 2 * R + 2];
+    // A_t (packed upper triangle) -> part2[0..NGm), h_t -> part2[NGm..NGm+R)
+    for (int idx = tid; idx < R * R; idx += nthr) {
+        const int j = idx / R, k = idx % R;
+        if (j <= k) {
+            const double gj = sh.g[j], gk = sh.g[k];
+            ps.part2[gram_off(R, j) + (k - j)] = t2[gram_off(R, j) + (k - j)] + (t2[NGm + j] * gk + gj * t2[NGm + k]) + kappa * gj * gk;
+        }
+    }
+    if (tid >= nthr - R) {
+        const int j = tid - (nthr - R);
+        ps.part2[NGm + j] = fma(psi, sh.g[j], t2[NGm + R + j]);
+    }
+    sync_n(nthr);
+    // bu = h - A xbar ; q1 = gamma - 2 xbar'h + xbar'A xbar   (warp 0)
+    if (tid < 32) {
+        const int lane = tid;
+        double ax = 0.0, hj = 0.0, xj = 0.0;
+        if (lane < R) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < R; k += 2) {
+                const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
+                a0 = fma(ps.part2[gram_off(R, lo) + hi - lo], sh.xb[k], a0);
+                if (k + 1 < R) {
+                    const int lo1 = k + 1 < lane ? k + 1 : lane, hi1 = k + 1 < lane ? lane : k + 1;
+                    a1 = fma(ps.part2[gram_off(R, lo1) + hi1 - lo1], sh.xb[k + 1], a1);
+                }
+            }
+            ax = a0 + a1;
+            hj = ps.part2[NGm + lane];
+            xj = sh.xb[lane];
+        }
+        const double xh = warp_allsum(xj * hj);
+        const double xax = warp_allsum(xj * ax);
+        const double w1 = sh.w1, w0 = sh.w0;
+        const double q1 = gamma - 2.0 * xh + xax;
+        const double q0 = t2[NGm + 2 * R + 3];
+        if (lane < R) sh.tot[NGm + lane] = w1 * (hj - ax);                     // b = w1 sum m e c
+        if (lane == 0) {
+            sh.tot[NGm + R + 0] = w1 * q1 + w0 * q0;                           // s = diff' Ri diff
+            sh.tot[NGm + R + 1] = q1;
+            sh.tot[NGm + R + 2] = q0;
+            sh.tot[NGm + R + 3] = t2[NGm + 2 * R + 4];
+        }
+    }
+    {
+        const double w1 = sh.w1;
+        for (int idx = tid; idx < NGm; idx += nthr) sh.tot[idx] = w1 * ps.part2[idx];   // G = w1 A_t
+    }
+    sync_n(nthr);
+}
+
 template <int R, typename T>
 __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KParams p) {
     using L = SlotLayout<R, T>;
-    constexpr int NSP = nstat_pad(R), NST = nstat(R);
-    constexpr int NCW = V2_CWARPS, NCT = NCW * 32;
+    constexpr int NSP2 = nstat2_pad(R), NST2 = nstat2(R);
+    constexpr int NCT = V2_CTRL_WARPS * 32;                     // control threads = tid 0..191
+    constexpr int NPW = V2_PASS_WARPS;
     extern __shared__ __align__(128) unsigned char dyn_smem_s[];
     __shared__ Smem<R> sh;
-    __shared__ __align__(8) uint64_t full[MAXSLOT];
-    __shared__ __align__(8) uint64_t done[MAXSLOT];
+    __shared__ __align__(8) PipeSmem<R> ps;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int series = blockIdx.x / p.cps;
@@ -240,6 +439,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     const int nt = te - tb;
     const bool writer = part == 0;
     const int nslot = p.nslot;
+    const int64_t n = p.n_steps;
 
     unsigned char* slots = dyn_smem_s;
     double* ebuf = reinterpret_cast<double*>(dyn_smem_s + (size_t)nslot * L::SLOT);
@@ -248,9 +448,14 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
 
     if (tid == 0) {
         for (int s = 0; s < nslot; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&done[s], L::TS);
+            mbar_init(&ps.full[s], 1);
+            mbar_init(&ps.done[s], L::TS);
         }
+        mbar_init(&ps.stats_full[0], NPW);
+        mbar_init(&ps.stats_full[1], NPW);
+        mbar_init(&ps.red_free, 1);
+        mbar_init(&ps.par_full[0], 1);
+        mbar_init(&ps.par_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < R * R; i += blockDim.x) {
@@ -271,50 +476,77 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     for (int i = tid; i < nt * TILE; i += blockDim.x) ebuf[i] = 0.0;
     __syncthreads();
 
-    if (warp == NCW) {                       // ---- producer warp ----
-        if (lane == 0) s_producer<R, T>(p, slots, full, done, Cs, series, tb, nt, nslot);
+    if (warp == V2_CWARPS) {                 // ---- producer warp ----
+        if (lane == 0) s_producer<R, T>(p, ps, slots, Cs, series, tb, nt, nslot);
         return;
     }
 
-    // ---- consumer warps ----
-    const bool masked = p.M != nullptr;
-    predict_cta<R>(p, sh, tid, p.k0, series, NCT);
-
-    for (int64_t t = 0; t < p.n_steps; ++t) {
-        T* Yrec_t = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + t * p.ldrec : nullptr;
-        stamp(p, t, 0);
-        s_warp_pass<R, T, false>(p, sh, ebuf, slots, full, done, Yrec_t, masked, tb, nt, nslot, t, warp, lane);
-        stamp(p, t, 1);
-        sync_n(NCT);
-        stamp(p, t, 2);
-        if (tid < NST) {                     // CTA partial: fixed order over the warps
-            double s = 0.0;
+    if (warp < V2_CTRL_WARPS) {
+        // ---- control warps: reduce + solve of step t while the pass warps run pass t+1 ----
+        predict_cta<R>(p, sh, tid, p.k0, series, NCT);                 // xbar_0, Pbar_0, a_0, w1/w0
+        if (tid < R) ps.xb0[tid] = sh.xb[tid];
+        __threadfence_block();
+        asm volatile("bar.arrive 2, %0;" ::"r"(NCT + NPW * 32) : "memory");     // xbar_0 is published
+        for (int64_t t = 0; t < n; ++t) {
+            stamp(p, t, 0);
+            mbar_wait(&ps.stats_full[t & 1], (uint32_t)((t >> 1) & 1));
+            stamp(p, t, 1);
+            if (tid < NST2) {                                           // CTA partial: fixed order over the pass warps
+                double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < NCW; ++w) s += sh.red[w * NSP + tid];
-            sh.part[tid] = s;
+                for (int w = 0; w < NPW; ++w) s += sh.red[w * NSP2 + tid];
+                ps.part2[tid] = s;
+            }
+            sync_n(NCT);
+            if (tid == 0) mbar_arrive(&ps.red_free);
+            stamp(p, t, 2);
+            grid_reduce<NST2, NSP2>(p, ps.part2, ps.tot2, tid, lane, warp, t, series, part, NCT);
+            stamp(p, t, 5);
+            assemble_stats<R>(sh, ps, tid, NCT);
+            small_update<R>(p, sh, tid, lane, warp, series, t, writer, NCT);
+            // publish g_t and xbar_{t+1} for pass t+2 (small_update ended with a barrier over the control threads)
+            if (tid < R) {
+                ps.par[t & 1][tid] = sh.g[tid];
+                ps.par[t & 1][R + tid] = sh.xb[tid];
+            }
+            sync_n(NCT);
+            if (tid == 0) mbar_arrive(&ps.par_full[t & 1]);
+            stamp(p, t, 6);
         }
-        grid_reduce<R>(p, sh, tid, lane, warp, t, series, part, NCT);
-        stamp(p, t, 5);
-        small_update<R>(p, sh, tid, lane, warp, series, t, writer, NCT);
-        stamp(p, t, 6);
+        if (writer) {
+            for (int i = tid; i < R * R; i += NCT) {
+                stg[st_P(R) + i] = sh.P[i];
+                stg[st_V(R) + i] = sh.V[i];
+                stg[st_Q(R) + i] = sh.Q[i];
+            }
+            if (tid < R) {
+                stg[st_x(R) + tid] = sh.x[tid];
+                if (p.grad_out != nullptr) p.grad_out[(int64_t)series * R + tid] = sh.grad[tid];
+            }
+            if (tid == 0) {
+                stg[st_rho(R)] = sh.rho;
+                stg[st_lam(R)] = sh.lam;
+            }
+        }
+        return;
     }
 
-    // flush pass: pending rank-1 update of the last step
-    s_warp_pass<R, T, true>(p, sh, ebuf, slots, full, done, (T*)nullptr, masked, tb, nt, nslot, p.n_steps, warp, lane);
-    if (writer) {
-        for (int i = tid; i < R * R; i += NCT) {
-            stg[st_P(R) + i] = sh.P[i];
-            stg[st_V(R) + i] = sh.V[i];
-            stg[st_Q(R) + i] = sh.Q[i];
-        }
-        if (tid < R) {
-            stg[st_x(R) + tid] = sh.x[tid];
-            if (p.grad_out != nullptr) p.grad_out[(int64_t)series * R + tid] = sh.grad[tid];
-        }
-        if (tid == 0) {
-            stg[st_rho(R)] = sh.rho;
-            stg[st_lam(R)] = sh.lam;
-        }
+    // ---- pass warps ----
+    const int wp = warp - V2_CTRL_WARPS;
+    const bool masked = p.M != nullptr;
+    asm volatile("bar.sync 2, %0;" ::"r"(NCT + NPW * 32) : "memory");   // xbar_0 available
+    for (int64_t pass = 0; pass < n; ++pass) {
+        // pass `pass` needs the solve of step pass-2 (g_{pass-2}, xbar_{pass-1})
+        if (pass >= 2) mbar_wait(&ps.par_full[(pass - 2) & 1], (uint32_t)(((pass - 2) >> 1) & 1));
+        T* Yrec_prev = (p.Yrec && pass >= 1) ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + (pass - 1) * p.ldrec : nullptr;
+        s_warp_pass<R, T, false>(p, ps, ebuf, slots, sh.red, Yrec_prev, masked, tb, nt, nslot, pass, wp, lane);
+    }
+    // flush: both pending rank-1 updates -> C_n; needs the solves of steps n-2 and n-1
+    if (n >= 2) mbar_wait(&ps.par_full[(n - 2) & 1], (uint32_t)(((n - 2) >> 1) & 1));
+    mbar_wait(&ps.par_full[(n - 1) & 1], (uint32_t)(((n - 1) >> 1) & 1));
+    {
+        T* Yrec_prev = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + (n - 1) * p.ldrec : nullptr;
+        s_warp_pass<R, T, true>(p, ps, ebuf, slots, sh.red, Yrec_prev, masked, tb, nt, nslot, n, wp, lane);
     }
 }
 
