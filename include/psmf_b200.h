@@ -137,7 +137,7 @@ int  psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* s
 int  psmf_launch_info2(psmf_handle h, int32_t* kernel, int32_t* nslot, int32_t* resident);
 
 /* debug: record globaltimer stamps of CTA 0 for the first `steps` filter steps of every following psmf_run
- * into dev_buf ([steps][8] uint64: pass start, pass end, after CTA sync, before grid barrier, after grid
+ * into dev_buf ([steps][16] uint64; entries 8.. are stamps of the first pass warp of the pipelined kernel: pass start, pass end, after CTA sync, before grid barrier, after grid
  * barrier, statistics reduced, step end, after the r x r solve).  dev_buf == NULL disables.           */
 int  psmf_set_trace(psmf_handle h, uint64_t* dev_buf, int32_t steps);
 

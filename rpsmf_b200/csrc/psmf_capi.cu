@@ -1,6 +1,7 @@
 // C ABI of the B200-native PSMF / rPSMF filter (include/psmf_b200.h).
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cstdint>
 #include <new>
 #include <string>
@@ -194,8 +195,7 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     if (cfg->kernel != 1 && e->d % 16 == 0) {
         const int TS = V2_TS;
         auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
-        // slot = C chunk + two time steps of y and m (software pipeline, psmf_stream.cuh SlotLayout)
-        const size_t slot = r128((size_t)TS * e->R * TILE * e->esize) + 2 * r128((size_t)TS * TILE * e->esize) + 2 * r128((size_t)TS * TILE);
+        const size_t slot = r128((size_t)TS * e->R * TILE * e->esize);     // psmf_stream.cuh SlotLayout: one chunk of C
         int cps2;
         if (e->S > 1) cps2 = 1;
         else if (cfg->ctas > 0) cps2 = cfg->ctas;
@@ -214,6 +214,10 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
             int64_t nslot = avail > 0 ? avail / (int64_t)slot : 0;
             if (nslot > nchunks_max) nslot = nchunks_max;
             if (nslot > 64) nslot = 64;
+            if (const char* ev = getenv("PSMF_NSLOT_MAX")) {            // debug knob
+                const int64_t cap = atoll(ev);
+                if (cap >= 2 && nslot > cap) nslot = cap;
+            }
             if (nslot >= (nchunks_max >= 2 ? 2 : 1)) {
                 e->cps2 = cps2;
                 e->nslot = (int)nslot;
@@ -353,6 +357,7 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     p.n_steps = n_steps; p.k0 = k0;
     p.n_series = h->S; p.cps = h->cps;
     p.flags = h->cfg.flags; p.dynamics = h->cfg.dynamics;
+    if (const char* ev = getenv("PSMF_DEBUG_FLAGS")) p.flags |= (int)strtol(ev, nullptr, 0) & (7 << 20);
     p.alpha = h->cfg.alpha; p.beta = h->cfg.beta;
     p.world = h->cfg.world_size; p.rank = h->cfg.rank;
     if (p.world > 1) {

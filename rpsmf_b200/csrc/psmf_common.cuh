@@ -22,6 +22,8 @@ constexpr int MAX_PEERS = 8;
 // flags (mirror include/psmf_b200.h)
 constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16, F_LL_STUDENT = 32;
 constexpr int DYN_IDENTITY = 0, DYN_COS = 1, DYN_EXTERNAL = 3;
+// debug-only flag bits (env PSMF_DEBUG_FLAGS, never set by the Python surface): results are WRONG with them
+constexpr int F_DBG_NOCOMPUTE = 1 << 20, F_DBG_NOSTORE = 1 << 21, F_DBG_NOYM = 1 << 22;
 
 // ---- tile layout and statistics vector ------------------------------------------------------------
 // Inside a 32-row tile, element (row i, column j) lives at  j*32 + (i ^ ((j & 7) << 2)).
@@ -39,6 +41,9 @@ __host__ __device__ constexpr int ngram(int R) { return R * (R + 1) / 2; }
 // statistics: packed upper triangle of G, then b (R), s, q1, q0, n_obs
 __host__ __device__ constexpr int nstat(int R) { return ngram(R) + R + 4; }
 __host__ __device__ constexpr int nstat_pad(int R) { return (nstat(R) + 7) / 8 * 8; }
+// pipelined kernel: packed upper triangle of A0, u (R), h0 (R), kappa, psi, gamma, q0, n_obs
+__host__ __device__ constexpr int nstat2(int R) { return ngram(R) + 2 * R + 5; }
+__host__ __device__ constexpr int nstat2_pad(int R) { return (nstat2(R) + 7) / 8 * 8; }
 // packed index of Gram entry (j, j) in row-major upper-triangular order
 __host__ __device__ constexpr int gram_off(int R, int j) { return j * R - j * (j - 1) / 2; }
 

@@ -40,7 +40,7 @@ struct Smem {
     double aug[2][R][2 * R + 2];   // double-buffered augmented matrix of the r x r solve
     double tot[NSP];
     double part[NSP];
-    double red[MAXW * NSP];        // per-warp partial statistics
+    double red[MAXW * nstat2_pad(R)];   // per-warp partial statistics (sized for the pipelined kernel's vector)
     double a, rho, lam;
     double w1, w0;                 // 1/(rho + a), 1/a : the only two values of w_i (rPSMF.py:92,98,32)
     double sc[8];                  // omega, eta, N, phi, sSe, alpha*phi, beta*omega
@@ -96,7 +96,15 @@ __device__ __forceinline__ void stamp(const KParams& p, int64_t t, int slot) {
     if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && t < p.trace_steps) {
         unsigned long long v;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
-        p.trace[t * 8 + slot] = v;
+        p.trace[t * 16 + slot] = v;
+    }
+}
+
+// debug stamps of the first pass warp (psmf_stream.cuh): slot 8.. of the 16-entry trace row
+__device__ __forceinline__ void stamp_pass(const KParams& p, int64_t t, int slot, unsigned long long v, bool timer) {
+    if (p.trace != nullptr && blockIdx.x == 0 && t < p.trace_steps) {
+        if (timer) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+        p.trace[t * 16 + slot] = v;
     }
 }
 
@@ -295,11 +303,11 @@ __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, i
 // row of largest |a_ik| -- found redundantly by every warp (no broadcast barrier) with one warp-wide
 // integer max over the high words of |a_ik| (16 mantissa bits decide, ties -> lowest row) -- and perm[k]
 // remembers it, so the solution row of unknown k is aug[R & 1][perm[k]].
-constexpr int GJ_THREADS = 192;
-template <int R>
+constexpr int GJ_THREADS = 192;                         // direct-load kernel; the pipelined kernel uses its control warps
+template <int R, int NGJ>
 __device__ void gauss_jordan_cta(Smem<R>& sh, int tid) {
     constexpr int NC = 2 * R + 1;
-    constexpr int TPR = GJ_THREADS / R;                 // threads per row
+    constexpr int TPR = NGJ / R;                        // threads per row
     constexpr int CPT = (NC + TPR - 1) / TPR;           // columns per thread
     const bool active = tid < R * TPR;
     const int i = active ? tid / TPR : 0;
@@ -334,12 +342,12 @@ __device__ void gauss_jordan_cta(Smem<R>& sh, int tid) {
                 sh.aug[nxt][i][c] = own[e];
             }
         }
-        named_bar_sync(1, GJ_THREADS);
+        named_bar_sync(1, NGJ);
     }
 }
 
 // ---- r x r part of the step (rPSMF.py:102-115,133-135), identical on every CTA; all `nthr` threads ----
-template <int R>
+template <int R, int NGJ>
 __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, int warp, int series, int64_t t,
                              bool writer, int nthr) {
     constexpr int NGm = ngram(R);
@@ -369,7 +377,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         sync_n(nthr);
         // the elimination is latency-bound: a subset of the warps runs it (less redundant pivot-search work on
         // the fp64 pipe, cheaper barrier), the others wait at the CTA barrier below
-        if (tid < GJ_THREADS) gauss_jordan_cta<R>(sh, tid);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
+        if (tid < NGJ) gauss_jordan_cta<R, NGJ>(sh, tid);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
         sync_n(nthr);
     }
     stamp(p, t, 7);
@@ -482,10 +490,10 @@ __device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restric
     const int parity = (int)((p.step_base + (unsigned long long)t) & 1ULL);
     const unsigned long long target = p.step_base + (unsigned long long)t + 1ULL;
     if (part == 0) {
-        if (tid < NST) {
-            const double v = tot[tid];
+        for (int e = tid; e < NST; e += nthr) {
+            const double v = tot[e];
             for (int pr = 0; pr < p.world; ++pr)
-                if (pr != p.rank) st_relaxed_sys_f64(p.mbox_peer[pr] + ((size_t)parity * MAX_PEERS + p.rank) * NSP + tid, v);
+                if (pr != p.rank) st_relaxed_sys_f64(p.mbox_peer[pr] + ((size_t)parity * MAX_PEERS + p.rank) * NSP + e, v);
         }
         __threadfence_system();
         sync_n(nthr);
@@ -498,14 +506,14 @@ __device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restric
         }
     }
     sync_n(nthr);
-    if (tid < NST) {
+    for (int e = tid; e < NST; e += nthr) {
         double s = 0.0;
         for (int src = 0; src < p.world; ++src)
-            s += (src == p.rank) ? tot[tid] : ld_relaxed_sys_f64(p.mbox_local + ((size_t)parity * MAX_PEERS + src) * NSP + tid);
-        tmp[tid] = s;
+            s += (src == p.rank) ? tot[e] : ld_relaxed_sys_f64(p.mbox_local + ((size_t)parity * MAX_PEERS + src) * NSP + e);
+        tmp[e] = s;
     }
     sync_n(nthr);
-    if (tid < NST) tot[tid] = tmp[tid];
+    for (int e = tid; e < NST; e += nthr) tot[e] = tmp[e];
     sync_n(nthr);
 }
 
@@ -518,7 +526,7 @@ template <int NST, int NSP>
 __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict__ part_v, double* __restrict__ tot, int tid,
                                             int lane, int warp, int64_t t, int series, int part, int nthr) {
     if (p.cps == 1) {
-        if (tid < NST) tot[tid] = part_v[tid];
+        for (int e = tid; e < NST; e += nthr) tot[e] = part_v[e];
         sync_n(nthr);
         if (p.world > 1) gpu_exchange<NST, NSP>(p, tot, part_v, tid, t, part, nthr);
         return;
@@ -527,23 +535,23 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
     const int cps = p.cps;
     if (cps <= 16) {
         double* mine = p.partials + ((size_t)parity * cps + part) * NSP;
-        if (tid < NST) mine[tid] = part_v[tid];
+        for (int e = tid; e < NST; e += nthr) mine[e] = part_v[e];
         stamp(p, t, 3);
         grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), nthr);
         stamp(p, t, 4);
         const double* basep = p.partials + (size_t)parity * cps * NSP;
-        if (tid < NST) {
+        for (int e = tid; e < NST; e += nthr) {
             double v[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = c < cps ? __ldcg(basep + (size_t)c * NSP + tid) : 0.0;
-            tot[tid] = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) +
-                          (((v[8] + v[9]) + (v[10] + v[11])) + ((v[12] + v[13]) + (v[14] + v[15])));
+            for (int c = 0; c < 16; ++c) v[c] = c < cps ? __ldcg(basep + (size_t)c * NSP + e) : 0.0;
+            tot[e] = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) +
+                     (((v[8] + v[9]) + (v[10] + v[11])) + ((v[12] + v[13]) + (v[14] + v[15])));
         }
     } else {
         const int pstr = (cps + 7) & ~7;
         double* pT = p.partials + (size_t)parity * NSP * (pstr + 1);
         double* totals = pT + (size_t)NSP * pstr;
-        if (tid < NST) pT[(size_t)tid * pstr + part] = part_v[tid];
+        for (int e = tid; e < NST; e += nthr) pT[(size_t)e * pstr + part] = part_v[e];
         stamp(p, t, 3);
         grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 1), nthr);
         const int nw = nthr >> 5;
@@ -564,7 +572,7 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
         }
         grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 2), nthr);
         stamp(p, t, 4);
-        if (tid < NST) tot[tid] = __ldcg(totals + tid);
+        for (int e = tid; e < NST; e += nthr) tot[e] = __ldcg(totals + e);
     }
     sync_n(nthr);
     if (p.world > 1) gpu_exchange<NST, NSP>(p, tot, part_v, tid, t, part, nthr);
@@ -657,7 +665,7 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
         }
         grid_reduce<NST, NSP>(p, sh.part, sh.tot, tid, lane, warp, t, series, part, blockDim.x);
         stamp(p, t, 5);
-        small_update<R>(p, sh, tid, lane, warp, series, t, writer, blockDim.x);
+        small_update<R, GJ_THREADS>(p, sh, tid, lane, warp, series, t, writer, blockDim.x);
         stamp(p, t, 6);
     }
 

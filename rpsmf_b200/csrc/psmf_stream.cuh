@@ -7,9 +7,9 @@
 //       1-D TMA path: UBLKCP in SASS) that complete on mbarriers, and bulk-stores updated chunks back.
 //       streaming (chunks of the CTA > slots): ring, every chunk loaded and stored once per step;
 //       resident  (chunks <= slots): C is loaded once, stays in shared memory for the whole launch.
-//   pass warps (9)   one warp per 32-row tile, all warps independent (psmf_filter.cuh: lane = row for the
+//   pass warps (12)  one warp per 32-row tile, all warps independent (psmf_filter.cuh: lane = row for the
 //       rank-1 update / y_hat / e, fp64 DMMA fragments for the Gram-type sums).
-//   control warps (6) CTA partial -> deterministic grid reduction (+ NVLink exchange) -> r x r solve.
+//   control warps (3) CTA partial -> deterministic grid reduction (+ NVLink exchange) -> r x r solve.
 //
 // Software pipeline.  The statistics of step t are sums over C_t = C_{t-1} + e_{t-1} g_{t-1}', and g_{t-1}
 // only exists after the solve of step t-1.  Expanding the rank-1 term,
@@ -34,26 +34,17 @@
 namespace psmf {
 
 constexpr int MAXSLOT = 64;
-constexpr int V2_CTRL_WARPS = 6;                                   // = GJ_THREADS / 32
-constexpr int V2_PASS_WARPS = V2_CWARPS - V2_CTRL_WARPS;           // 9
-static_assert(V2_CTRL_WARPS * 32 == GJ_THREADS, "control warps run the Gauss-Jordan");
+constexpr int V2_CTRL_WARPS = 3;                                   // reduction + r x r solve
+constexpr int V2_PASS_WARPS = V2_CWARPS - V2_CTRL_WARPS;           // 12: one tile takes a warp ~1.6 us
 
 __host__ __device__ constexpr int s_threads() { return (V2_CWARPS + 1) * 32; }
-// pipelined statistics: packed upper triangle of A0, u (R), h0 (R), kappa, psi, gamma, q0, n_obs
-__host__ __device__ constexpr int nstat2(int R) { return ngram(R) + 2 * R + 5; }
-__host__ __device__ constexpr int nstat2_pad(int R) { return (nstat2(R) + 7) / 8 * 8; }
 
 __host__ __device__ constexpr size_t round128(size_t x) { return (x + 127) / 128 * 128; }
 template <int R, typename T>
 struct SlotLayout {
     static constexpr int TS = V2_TS;
     static constexpr size_t TILE_BYTES = (size_t)R * TILE * sizeof(T);
-    static constexpr size_t CB = round128(TS * TILE_BYTES);
-    static constexpr size_t YB1 = round128((size_t)TS * TILE * sizeof(T));   // one time step of y for the chunk
-    static constexpr size_t MB1 = round128((size_t)TS * TILE);               // one time step of m
-    static constexpr size_t YOFF = CB;                                       // y region of parity b at YOFF + b*YB1
-    static constexpr size_t MOFF = CB + 2 * YB1;
-    static constexpr size_t SLOT = CB + 2 * YB1 + 2 * MB1;
+    static constexpr size_t SLOT = round128(TS * TILE_BYTES);     // a slot holds one chunk of C, nothing else
 };
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------------
@@ -139,10 +130,37 @@ struct PassAcc {
 // ---- pass warp: pass `pass` over the tiles tl = wp, wp + NPW, ... of the CTA ---------------------------
 //   pass p in [0, n):  C_{p-2} -> C_{p-1} in the slot, e_{p-1} -> ebuf, Yrec_{p-1}, sums for step p
 //   pass n (FLUSH):    C_{n-2} -> C_n (both pending rank-1 updates), Yrec_{n-1}
+// y / m of steps p-1 and p are read with coalesced global loads, prefetched one tile ahead (the producer
+// thread is latency-bound per bulk operation, so the slots carry C only).
+template <typename T>
+struct YM {
+    double yp, yc;       // y_{p-1}[row], y_p[row]   (0 outside the shard)
+    bool mp, mc;         // m_{p-1}[row], m_p[row]
+};
+template <typename T>
+__device__ __forceinline__ YM<T> load_ym(const KParams& p, const T* __restrict__ Yb, const uint8_t* __restrict__ Mb, int64_t pass,
+                                         int64_t row, bool has_prev, bool has_cur) {
+    YM<T> r;
+    const bool inb = row < p.d;
+    r.yp = 0.0; r.yc = 0.0; r.mp = inb; r.mc = inb;
+    if (inb) {
+        if (has_prev) {
+            r.yp = (double)__ldg(Yb + (pass - 1) * p.ldy + row);
+            if (Mb != nullptr) r.mp = __ldg(Mb + (pass - 1) * p.ldm + row) != 0;
+        }
+        if (has_cur) {
+            r.yc = (double)__ldg(Yb + pass * p.ldy + row);
+            if (Mb != nullptr) r.mc = __ldg(Mb + pass * p.ldm + row) != 0;
+        }
+    }
+    return r;
+}
+
 template <int R, typename T, bool FLUSH>
 __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, double* __restrict__ ebuf,
                                             unsigned char* __restrict__ slots, double* __restrict__ red, T* __restrict__ Yrec_prev,
-                                            bool masked, int tb, int nt, int nslot, int64_t pass, int wp, int lane) {
+                                            const T* __restrict__ Yb, const uint8_t* __restrict__ Mb, int tb, int nt, int nslot,
+                                            int64_t pass, int wp, int lane) {
     using L = SlotLayout<R, T>;
     constexpr int TS = L::TS, NSP2 = nstat2_pad(R);
     const int nchunks = (nt + TS - 1) / TS;
@@ -151,26 +169,38 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
     const double* gp = (pass >= 2) ? ps.par[(pass - 2) & 1] : ps.xb0;
     const double* xbp = (pass >= 2) ? ps.par[(pass - 2) & 1] + R : ps.xb0;
     const double* gl = ps.par[(pass - 1) & 1];                          // g_{n-1} (flush only)
-    const int ycur = (int)(pass & 1), yprev = ycur ^ 1;
+    const bool has_prev = pass >= 1, has_cur = !FLUSH;
     PassAcc acc;
     acc.zero();
+    long long wait_full = 0;
 
+    YM<T> nx = load_ym<T>(p, Yb, Mb, pass, (int64_t)(tb + wp) * TILE + lane, has_prev, has_cur);
     for (int tl = wp; tl < nt; tl += V2_PASS_WARPS) {
+        const YM<T> ym = nx;
+        if (tl + V2_PASS_WARPS < nt)                                   // prefetch y / m of this warp's next tile
+            nx = load_ym<T>(p, Yb, Mb, pass, (int64_t)(tb + tl + V2_PASS_WARPS) * TILE + lane, has_prev, has_cur);
         const int k = tl / TS, i = tl - k * TS;
         const int64_t kk = pass * nchunks + k;
         const int slot = streaming ? (int)(kk % nslot) : k;
         const uint32_t parity = (uint32_t)((streaming ? kk / nslot : pass) & 1);
         unsigned char* sb = slots + (size_t)slot * L::SLOT;
+        const long long c0 = clock64();
         mbar_wait(&ps.full[slot], parity);
+        wait_full += clock64() - c0;
         const int64_t row = (int64_t)(tb + tl) * TILE + lane;
         const int rl = tl * TILE + lane;
         const bool inb = row < p.d;
         T* tile = reinterpret_cast<T*>(sb) + (size_t)i * (R * TILE);
-        const T* yp_s = reinterpret_cast<const T*>(sb + L::YOFF + yprev * L::YB1) + i * TILE;
-        const T* yc_s = reinterpret_cast<const T*>(sb + L::YOFF + ycur * L::YB1) + i * TILE;
-        const unsigned char* mp_s = sb + L::MOFF + yprev * L::MB1 + i * TILE;
-        const unsigned char* mc_s = sb + L::MOFF + ycur * L::MB1 + i * TILE;
 
+        if ((p.flags & F_DBG_NOCOMPUTE) != 0) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const int ntc = min(TS, nt - k * TS);
+                mbar_arrive_n(&ps.done[slot], (i == ntc - 1) ? (uint32_t)(TS - ntc + 1) : 1u);
+            }
+            continue;
+        }
         // ---- phase 1, lane = row ----
         double c[R];
 #pragma unroll
@@ -186,10 +216,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
 #pragma unroll
             for (int j = 0; j < R; ++j) yh4[j & 3] = fma(c[j], xbp[j], yh4[j & 3]);     // rPSMF.py:89
             const double yh = (yh4[0] + yh4[1]) + (yh4[2] + yh4[3]);
-            bool mprev = inb;
-            if (masked && inb) mprev = mp_s[lane] != 0;
-            const double yprv = inb ? (double)yp_s[lane] : 0.0;
-            e = yprv - (mprev ? yh : 0.0);                         // rPSMF.py:101
+            e = ym.yp - (ym.mp ? yh : 0.0);                        // rPSMF.py:101
             if (Yrec_prev != nullptr && inb) Yrec_prev[row] = (T)yh;
         }
         if constexpr (FLUSH) {                                     // C_n = C_{n-1} + e_{n-1} g_{n-1}'
@@ -201,17 +228,17 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
 #pragma unroll
             for (int j = 0; j < R; ++j) tile[tile_pos(j, lane)] = (T)c[j];
             ebuf[rl] = e;
-            bool mi = inb;
-            if (masked && inb) mi = mc_s[lane] != 0;
-            const double yi = inb ? (double)yc_s[lane] : 0.0;
+            const bool mi = ym.mc;
+            const double yi = ym.yc;
             acc.v[0] += mi ? e * e : 0.0;                          // kappa
             acc.v[1] += mi ? yi * e : 0.0;                         // psi
             acc.v[2] += mi ? yi * yi : 0.0;                        // gamma
             acc.v[3] += mi ? 0.0 : yi * yi;                        // q0 (rows missing at step p: e_p = y_p)
             acc.v[4] += mi ? 1.0 : 0.0;                            // n_obs
-            const unsigned mbits = __ballot_sync(FULL, mi);
+            const double me = mi ? e : 0.0, my = mi ? yi : 0.0;   // B columns 0 / 1 of the [u | h0] product
             __syncwarp();
             // ---- phase 2: A0 += sum m c c', [u | h0] += sum m c [e, y]  (fp64 DMMA, k = row) ----
+            const unsigned mbits = __ballot_sync(FULL, mi);
             const int kq = lane & 3, mm = lane >> 2;
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
@@ -220,9 +247,8 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
                 const int pos = r4 ^ (mm << 2);
                 const double a0 = (mm < R) ? (double)tile[mm * 32 + pos] : 0.0;
                 const double b0 = mrow ? a0 : 0.0;
-                double bx = 0.0;                                   // B columns 0 / 1 = m e_{p-1} / m y_p
-                if (mm == 0) bx = mrow ? ebuf[tl * TILE + r4] : 0.0;
-                if (mm == 1) bx = (mrow && (int64_t)(tb + tl) * TILE + r4 < p.d) ? (double)yc_s[r4] : 0.0;
+                const double se = __shfl_sync(FULL, me, r4), sy = __shfl_sync(FULL, my, r4);
+                const double bx = (mm == 0) ? se : ((mm == 1) ? sy : 0.0);
                 dmma884(acc.g00, a0, b0);
                 dmma884(acc.u0, a0, bx);
                 if constexpr (R > 8) {
@@ -244,6 +270,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
         }
     }
     if constexpr (!FLUSH) {
+        if (wp == 0 && lane == 0) stamp_pass(p, pass, 10, (unsigned long long)wait_full, false);
         // the control warps have consumed the partial sums of the previous pass
         if (pass >= 1) mbar_wait(&ps.red_free, (uint32_t)((pass - 1) & 1));
         double* r0 = red + wp * NSP2;
@@ -277,84 +304,69 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
     }
 }
 
-// ---- producer: one thread drives all bulk copies of the CTA -------------------------------------------
+// ---- producer: one thread drives all bulk copies of the CTA (C chunks only) ------------------------------
+// The loop is latency-bound per iteration (~0.6 us measured, scratch/bulkbench.cu): one bulk store and one
+// bulk load of a 16 KB chunk per iteration is what sustains the HBM rate, so nothing else goes through it.
 template <int R, typename T>
-__device__ void s_producer(const KParams& p, PipeSmem<R>& ps, unsigned char* slots, T* Cs, int series, int tb, int nt,
-                           int nslot) {
+__device__ void s_producer(const KParams& p, PipeSmem<R>& ps, unsigned char* slots, T* Cs, int tb, int nt, int nslot) {
     using L = SlotLayout<R, T>;
     constexpr int TS = L::TS;
     const int nchunks = (nt + TS - 1) / TS;
     const bool streaming = nchunks > nslot;
     const int64_t npass = p.n_steps + 1;
-    const bool masked = p.M != nullptr;
-    const T* Yb = reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst;
-    const uint8_t* Mb = masked ? p.M + (int64_t)series * p.msst : nullptr;
-    int64_t kk = 0;
-    for (int64_t pass = 0; pass < npass; ++pass) {
-        const bool last = pass == p.n_steps;
-        // y/m of the current step go to region (pass & 1); the other region already holds y_{pass-1} in the
-        // resident regime (slots persist) and is reloaded in the streaming regime
-        const bool load_cur = !last;
-        const bool load_prev = streaming && pass >= 1;
-        for (int k = 0; k < nchunks; ++k, ++kk) {
-            const int slot = streaming ? (int)(kk % nslot) : k;
-            const int64_t use = streaming ? kk / nslot : pass;
-            unsigned char* sb = slots + (size_t)slot * L::SLOT;
-            if (use > 0) {
-                mbar_wait(&ps.done[slot], (uint32_t)((use - 1) & 1));     // pass warps released the previous occupant
-                if (streaming) {
-                    const int pk = (int)((kk - nslot) % nchunks);
-                    const int ptiles = min(TS, nt - pk * TS);
-                    bulk_store(Cs + (size_t)(tb + pk * TS) * (R * TILE), sb, (uint32_t)(ptiles * L::TILE_BYTES));
-                    bulk_commit();
-                    bulk_wait_read<0>();                                   // slot may be overwritten
-                    // the chunk loaded below was stored (nchunks - nslot) groups ago: make sure that store has
-                    // fully completed before reading it back
-                    if (nchunks - nslot >= 2) bulk_wait<2>(); else bulk_wait<0>();
-                }
-            }
-            const int ntc = min(TS, nt - k * TS);
-            const int64_t row0 = (int64_t)(tb + k * TS) * TILE;
-            int64_t vrows = p.d - row0;
-            vrows = vrows < 0 ? 0 : (vrows > (int64_t)ntc * TILE ? (int64_t)ntc * TILE : vrows);
-            const bool loadC = streaming || pass == 0;
-            const uint32_t cbytes = loadC ? (uint32_t)(ntc * L::TILE_BYTES) : 0u;
-            const uint32_t ybytes = (uint32_t)(vrows * sizeof(T));
-            const uint32_t mbytes = masked ? (uint32_t)vrows : 0u;
-            const uint32_t tx = cbytes + (load_cur ? ybytes + mbytes : 0u) + (load_prev ? ybytes + mbytes : 0u);
-            if (tx == 0) {
-                mbar_arrive(&ps.full[slot]);
-            } else {
-                mbar_arrive_expect_tx(&ps.full[slot], tx);
-                if (cbytes) bulk_load(sb, Cs + (size_t)(tb + k * TS) * (R * TILE), cbytes, &ps.full[slot]);
-                if (load_cur && ybytes) {
-                    const int b = (int)(pass & 1);
-                    bulk_load(sb + L::YOFF + b * L::YB1, Yb + pass * p.ldy + row0, ybytes, &ps.full[slot]);
-                    if (mbytes) bulk_load(sb + L::MOFF + b * L::MB1, Mb + pass * p.ldm + row0, mbytes, &ps.full[slot]);
-                }
-                if (load_prev && ybytes) {
-                    const int b = (int)((pass - 1) & 1);
-                    bulk_load(sb + L::YOFF + b * L::YB1, Yb + (pass - 1) * p.ldy + row0, ybytes, &ps.full[slot]);
-                    if (mbytes) bulk_load(sb + L::MOFF + b * L::MB1, Mb + (pass - 1) * p.ldm + row0, mbytes, &ps.full[slot]);
-                }
-            }
-        }
-    }
-    // drain: store what is still only in shared memory
+    const uint32_t last_bytes = (uint32_t)((nt - (nchunks - 1) * TS) * L::TILE_BYTES);
+    const uint32_t full_bytes = (uint32_t)(TS * L::TILE_BYTES);
+    T* Cb = Cs + (size_t)tb * (R * TILE);
+    constexpr size_t CHUNK_ELEMS = (size_t)TS * R * TILE;
     if (streaming) {
-        for (int64_t j = kk - nslot; j < kk; ++j) {
-            const int slot = (int)(j % nslot);
-            mbar_wait(&ps.done[slot], (uint32_t)((j / nslot) & 1));
-            const int pk = (int)(j % nchunks);
-            const int ptiles = min(TS, nt - pk * TS);
-            bulk_store(Cs + (size_t)(tb + pk * TS) * (R * TILE), slots + (size_t)slot * L::SLOT, (uint32_t)(ptiles * L::TILE_BYTES));
+        // Ring of nslot slots over the chunk sequence (consumption order: pass-major).  Chunk j is stored as soon
+        // as the pass warps release it and its slot is reloaded with chunk j + nslot right after the store has
+        // left shared memory.
+        const int64_t total = npass * nchunks;
+        const int lag = nchunks - nslot + 1;          // >= 2: store groups issued after the previous version of a chunk
+        int lk = 0;                                   // chunk-in-pass index of the next load
+        int64_t lc = 0;                               // global index of the next load
+        for (; lc < total && lc < nslot; ++lc) {
+            const uint32_t bytes = lk == nchunks - 1 ? last_bytes : full_bytes;
+            mbar_arrive_expect_tx(&ps.full[lc], bytes);
+            bulk_load(slots + (size_t)lc * L::SLOT, Cb + (size_t)lk * CHUNK_ELEMS, bytes, &ps.full[lc]);
+            if (++lk == nchunks) lk = 0;
+        }
+        int sk = 0, slot = 0;                         // chunk-in-pass index / slot of the next store
+        uint32_t par = 0;
+        for (int64_t j = 0; j < total; ++j) {
+            mbar_wait(&ps.done[slot], par);                                       // chunk j processed
+            unsigned char* sb = slots + (size_t)slot * L::SLOT;
+            if ((p.flags & F_DBG_NOSTORE) == 0)
+                bulk_store(Cb + (size_t)sk * CHUNK_ELEMS, sb, sk == nchunks - 1 ? last_bytes : full_bytes);
             bulk_commit();
+            if (lc < total) {
+                bulk_wait_read<0>();                                               // the store has left shared memory
+                // the previous version of the chunk loaded now (one pass ago) was stored `lag` groups ago
+                if (lag >= 8) bulk_wait<8>(); else if (lag >= 4) bulk_wait<4>(); else if (lag >= 2) bulk_wait<2>(); else bulk_wait<0>();
+                const uint32_t bytes = lk == nchunks - 1 ? last_bytes : full_bytes;
+                mbar_arrive_expect_tx(&ps.full[slot], bytes);
+                bulk_load(sb, Cb + (size_t)lk * CHUNK_ELEMS, bytes, &ps.full[slot]);
+                if (++lk == nchunks) lk = 0;
+                ++lc;
+            }
+            if (++sk == nchunks) sk = 0;
+            if (++slot == nslot) { slot = 0; par ^= 1u; }
         }
     } else {
         for (int k = 0; k < nchunks; ++k) {
+            const uint32_t bytes = k == nchunks - 1 ? last_bytes : full_bytes;
+            mbar_arrive_expect_tx(&ps.full[k], bytes);
+            bulk_load(slots + (size_t)k * L::SLOT, Cb + (size_t)k * CHUNK_ELEMS, bytes, &ps.full[k]);
+        }
+        for (int64_t pass = 1; pass < npass; ++pass)
+            for (int k = 0; k < nchunks; ++k) {
+                mbar_wait(&ps.done[k], (uint32_t)((pass - 1) & 1));               // pass warps are done with pass-1
+                mbar_arrive(&ps.full[k]);                                          // C stays resident
+            }
+        for (int k = 0; k < nchunks; ++k) {
             mbar_wait(&ps.done[k], (uint32_t)((npass - 1) & 1));
-            const int ptiles = min(TS, nt - k * TS);
-            bulk_store(Cs + (size_t)(tb + k * TS) * (R * TILE), slots + (size_t)k * L::SLOT, (uint32_t)(ptiles * L::TILE_BYTES));
+            bulk_store(Cb + (size_t)k * CHUNK_ELEMS, slots + (size_t)k * L::SLOT, k == nchunks - 1 ? last_bytes : full_bytes);
             bulk_commit();
         }
     }
@@ -477,7 +489,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     __syncthreads();
 
     if (warp == V2_CWARPS) {                 // ---- producer warp ----
-        if (lane == 0) s_producer<R, T>(p, ps, slots, Cs, series, tb, nt, nslot);
+        if (lane == 0) s_producer<R, T>(p, ps, slots, Cs, tb, nt, nslot);
         return;
     }
 
@@ -491,11 +503,11 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
             stamp(p, t, 0);
             mbar_wait(&ps.stats_full[t & 1], (uint32_t)((t >> 1) & 1));
             stamp(p, t, 1);
-            if (tid < NST2) {                                           // CTA partial: fixed order over the pass warps
+            for (int e = tid; e < NST2; e += NCT) {                     // CTA partial: fixed order over the pass warps
                 double s = 0.0;
 #pragma unroll
-                for (int w = 0; w < NPW; ++w) s += sh.red[w * NSP2 + tid];
-                ps.part2[tid] = s;
+                for (int w = 0; w < NPW; ++w) s += sh.red[w * NSP2 + e];
+                ps.part2[e] = s;
             }
             sync_n(NCT);
             if (tid == 0) mbar_arrive(&ps.red_free);
@@ -503,7 +515,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
             grid_reduce<NST2, NSP2>(p, ps.part2, ps.tot2, tid, lane, warp, t, series, part, NCT);
             stamp(p, t, 5);
             assemble_stats<R>(sh, ps, tid, NCT);
-            small_update<R>(p, sh, tid, lane, warp, series, t, writer, NCT);
+            small_update<R, NCT>(p, sh, tid, lane, warp, series, t, writer, NCT);
             // publish g_t and xbar_{t+1} for pass t+2 (small_update ended with a barrier over the control threads)
             if (tid < R) {
                 ps.par[t & 1][tid] = sh.g[tid];
@@ -533,20 +545,24 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
 
     // ---- pass warps ----
     const int wp = warp - V2_CTRL_WARPS;
-    const bool masked = p.M != nullptr;
+    const T* Yb = reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst;
+    const uint8_t* Mb = p.M != nullptr ? p.M + (int64_t)series * p.msst : nullptr;
     asm volatile("bar.sync 2, %0;" ::"r"(NCT + NPW * 32) : "memory");   // xbar_0 available
     for (int64_t pass = 0; pass < n; ++pass) {
         // pass `pass` needs the solve of step pass-2 (g_{pass-2}, xbar_{pass-1})
+        if (wp == 0 && lane == 0) stamp_pass(p, pass, 11, 0, true);
         if (pass >= 2) mbar_wait(&ps.par_full[(pass - 2) & 1], (uint32_t)(((pass - 2) >> 1) & 1));
+        if (wp == 0 && lane == 0) stamp_pass(p, pass, 8, 0, true);
         T* Yrec_prev = (p.Yrec && pass >= 1) ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + (pass - 1) * p.ldrec : nullptr;
-        s_warp_pass<R, T, false>(p, ps, ebuf, slots, sh.red, Yrec_prev, masked, tb, nt, nslot, pass, wp, lane);
+        s_warp_pass<R, T, false>(p, ps, ebuf, slots, sh.red, Yrec_prev, Yb, Mb, tb, nt, nslot, pass, wp, lane);
+        if (wp == 0 && lane == 0) stamp_pass(p, pass, 9, 0, true);
     }
     // flush: both pending rank-1 updates -> C_n; needs the solves of steps n-2 and n-1
     if (n >= 2) mbar_wait(&ps.par_full[(n - 2) & 1], (uint32_t)(((n - 2) >> 1) & 1));
     mbar_wait(&ps.par_full[(n - 1) & 1], (uint32_t)(((n - 1) >> 1) & 1));
     {
         T* Yrec_prev = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + (n - 1) * p.ldrec : nullptr;
-        s_warp_pass<R, T, true>(p, ps, ebuf, slots, sh.red, Yrec_prev, masked, tb, nt, nslot, n, wp, lane);
+        s_warp_pass<R, T, true>(p, ps, ebuf, slots, sh.red, Yrec_prev, Yb, Mb, tb, nt, nslot, n, wp, lane);
     }
 }
 

@@ -22,3 +22,7 @@ step = t[1:, 0] - t[:-1, 0]
 print("d=%d kernel=%d  step mean %.2f us" % (d, kernel, step.mean() / 1e3))
 for n, v in zip(["pass", "cta_sync", "partials", "grid_barrier", "tot_reduce", "gauss_jordan", "small_rest"], dts.mean(0)):
     print("  %-14s %8.2f us" % (n, v / 1e3))
+
+if kernel == 2:
+    pw = t[:, 9] - t[:, 8]; pwait = t[:, 8] - t[:, 11]; wf = t[:, 10]
+    print("  pass warp 0: pass %.2f us, wait for solve(t-2) %.2f us, cycles waiting for slots %.0f (%.2f us @1.9GHz)" % (pw.mean()/1e3, pwait.mean()/1e3, wf.mean(), wf.mean()/1.9e3))
