@@ -133,24 +133,23 @@ struct PassAcc {
 // y / m of steps p-1 and p are read with coalesced global loads, prefetched one tile ahead (the producer
 // thread is latency-bound per bulk operation, so the slots carry C only).
 template <typename T>
-struct YM {
-    double yp, yc;       // y_{p-1}[row], y_p[row]   (0 outside the shard)
-    bool mp, mc;         // m_{p-1}[row], m_p[row]
+struct YM {              // RAW loaded values: converting at load time would stall on the load right away
+    T yp, yc;            // y_{p-1}[row], y_p[row]
+    unsigned char mp, mc;
 };
 template <typename T>
 __device__ __forceinline__ YM<T> load_ym(const KParams& p, const T* __restrict__ Yb, const uint8_t* __restrict__ Mb, int64_t pass,
                                          int64_t row, bool has_prev, bool has_cur) {
     YM<T> r;
-    const bool inb = row < p.d;
-    r.yp = 0.0; r.yc = 0.0; r.mp = inb; r.mc = inb;
-    if (inb) {
+    r.yp = (T)0; r.yc = (T)0; r.mp = 1; r.mc = 1;
+    if (row < p.d) {
         if (has_prev) {
-            r.yp = (double)__ldg(Yb + (pass - 1) * p.ldy + row);
-            if (Mb != nullptr) r.mp = __ldg(Mb + (pass - 1) * p.ldm + row) != 0;
+            r.yp = __ldg(Yb + (pass - 1) * p.ldy + row);
+            if (Mb != nullptr) r.mp = __ldg(Mb + (pass - 1) * p.ldm + row);
         }
         if (has_cur) {
-            r.yc = (double)__ldg(Yb + pass * p.ldy + row);
-            if (Mb != nullptr) r.mc = __ldg(Mb + pass * p.ldm + row) != 0;
+            r.yc = __ldg(Yb + pass * p.ldy + row);
+            if (Mb != nullptr) r.mc = __ldg(Mb + pass * p.ldm + row);
         }
     }
     return r;
@@ -216,7 +215,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
 #pragma unroll
             for (int j = 0; j < R; ++j) yh4[j & 3] = fma(c[j], xbp[j], yh4[j & 3]);     // rPSMF.py:89
             const double yh = (yh4[0] + yh4[1]) + (yh4[2] + yh4[3]);
-            e = ym.yp - (ym.mp ? yh : 0.0);                        // rPSMF.py:101
+            e = (double)ym.yp - ((inb && ym.mp != 0) ? yh : 0.0);  // rPSMF.py:101
             if (Yrec_prev != nullptr && inb) Yrec_prev[row] = (T)yh;
         }
         if constexpr (FLUSH) {                                     // C_n = C_{n-1} + e_{n-1} g_{n-1}'
@@ -228,8 +227,8 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
 #pragma unroll
             for (int j = 0; j < R; ++j) tile[tile_pos(j, lane)] = (T)c[j];
             ebuf[rl] = e;
-            const bool mi = ym.mc;
-            const double yi = ym.yc;
+            const bool mi = inb && ym.mc != 0;
+            const double yi = (double)ym.yc;
             acc.v[0] += mi ? e * e : 0.0;                          // kappa
             acc.v[1] += mi ? yi * e : 0.0;                         // psi
             acc.v[2] += mi ? yi * yi : 0.0;                        // gamma
