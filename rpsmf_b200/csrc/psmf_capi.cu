@@ -386,6 +386,7 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     if (use2) {
         p.cps = h->cps2;
         p.nslot = h->nslot;
+        p.nsolve = h->resident2 ? 5 : 2;
         CK(h, LAUNCH_S[h->R](p, h->cfg.dtype, h->S * h->cps2, h->dyn_smem2, st, h->cps2 > 1));
         h->last_kernel = 2;
     } else {

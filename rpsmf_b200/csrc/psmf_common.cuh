@@ -35,7 +35,7 @@ __host__ __device__ constexpr int tile_pos(int j, int i) { return j * 32 + (i ^ 
 constexpr int V1_WARPS = 8;     // direct-load kernel: warps per CTA (one tile per warp at a time)
 constexpr int V2_CWARPS = 15;   // TMA-staged kernel: consumer warps (+1 producer warp)
 constexpr int V2_TS = 4;        // TMA-staged kernel: tiles per shared-memory chunk slot
-constexpr int MAXW = 15;        // max consumer warps of any kernel (sizes the per-warp partial buffer)
+constexpr int MAXW = 12;        // max warps that write per-warp partial statistics in any kernel
 
 __host__ __device__ constexpr int ngram(int R) { return R * (R + 1) / 2; }
 // statistics: packed upper triangle of G, then b (R), s, q1, q0, n_obs
@@ -85,6 +85,7 @@ struct KParams {
     unsigned long long step_base;
     // streaming kernel
     int32_t nslot;            // shared-memory chunk slots per CTA
+    int32_t nsolve;           // solver warps of the pipelined kernel (2: streaming, 5: resident)
     int32_t trace_steps;      // debug: number of steps recorded in `trace`
     unsigned long long* trace; // debug: [trace_steps][8] globaltimer stamps of CTA 0 (or nullptr)
 };

@@ -78,17 +78,19 @@ __device__ __forceinline__ void red_release_gpu(unsigned long long* p, unsigned 
 
 // barrier 0 over the first `n` threads of the CTA (n == blockDim.x: plain __syncthreads; the streaming
 // kernel excludes its producer warp)
-__device__ __forceinline__ void sync_n(int n) { asm volatile("bar.sync 0, %0;" ::"r"(n) : "memory"); }
+template <int BAR = 0>
+__device__ __forceinline__ void sync_n(int n) { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "r"(n) : "memory"); }
 
 // All CTAs of the grid are co-resident (cooperative launch).  `target` grows monotonically.
-__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target, int nthr) {
-    sync_n(nthr);
-    if (threadIdx.x == 0) {
+template <int BAR = 0>
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target, int nthr, int tid) {
+    sync_n<BAR>(nthr);
+    if (tid == 0) {
         red_release_gpu(bar, 1ULL);
         while (ld_acquire_gpu(bar) < target) {
         }
     }
-    sync_n(nthr);
+    sync_n<BAR>(nthr);
 }
 
 // debug phase stamps (CTA 0, thread 0): enabled when KParams.trace != nullptr
@@ -233,7 +235,7 @@ __device__ __forceinline__ void acc_writeout(TileAcc<R>& A, double* __restrict__
 }
 
 // ---- predict half: x_bar = f(x), P_bar = F P F' + Q, V x_bar, a (all `nthr` threads; ends with a barrier) ----
-template <int R>
+template <int R, int BAR = 0>
 __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, int series, int nthr) {
     const bool simp = (p.flags & F_SIMPLIFIED) != 0;
     const int lane = tid & 31;
@@ -251,7 +253,7 @@ __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, i
         sh.xb[tid] = xb;
         sh.fd[tid] = fd;
     }
-    sync_n(nthr);
+    sync_n<BAR>(nthr);
     if (tid >= nthr - 32) {
         // last warp: V x_bar, V' x_bar, a = x_bar' V x_bar and the two possible row weights
         double v = 0.0;
@@ -293,7 +295,7 @@ __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, i
         }
         sh.Pb[idx] = pb;
     }
-    sync_n(nthr);
+    sync_n<BAR>(nthr);
 }
 
 // Gauss-Jordan with partial pivoting on the R x (2R+1) augmented matrix [I + Pbar G | Pbar | Pbar b], run by
@@ -304,7 +306,7 @@ __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, i
 // integer max over the high words of |a_ik| (16 mantissa bits decide, ties -> lowest row) -- and perm[k]
 // remembers it, so the solution row of unknown k is aug[R & 1][perm[k]].
 constexpr int GJ_THREADS = 192;                         // direct-load kernel; the pipelined kernel uses its control warps
-template <int R, int NGJ>
+template <int R, int NGJ, int GJBAR = 1>
 __device__ void gauss_jordan_cta(Smem<R>& sh, int tid) {
     constexpr int NC = 2 * R + 1;
     constexpr int TPR = NGJ / R;                        // threads per row
@@ -342,12 +344,12 @@ __device__ void gauss_jordan_cta(Smem<R>& sh, int tid) {
                 sh.aug[nxt][i][c] = own[e];
             }
         }
-        named_bar_sync(1, NGJ);
+        named_bar_sync(GJBAR, NGJ);
     }
 }
 
 // ---- r x r part of the step (rPSMF.py:102-115,133-135), identical on every CTA; all `nthr` threads ----
-template <int R, int NGJ>
+template <int R, int NGJ, int BAR = 0, int GJBAR = 1>
 __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, int warp, int series, int64_t t,
                              bool writer, int nthr) {
     constexpr int NGm = ngram(R);
@@ -374,11 +376,11 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
             for (int k = 0; k < R; ++k) acc = fma(sh.Pb[i * R + k], tot[NGm + k], acc);
             sh.aug[0][i][2 * R] = acc;
         }
-        sync_n(nthr);
+        sync_n<BAR>(nthr);
         // the elimination is latency-bound: a subset of the warps runs it (less redundant pivot-search work on
         // the fp64 pipe, cheaper barrier), the others wait at the CTA barrier below
-        if (tid < NGJ) gauss_jordan_cta<R, NGJ>(sh, tid);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
-        sync_n(nthr);
+        if (tid < NGJ) gauss_jordan_cta<R, NGJ, GJBAR>(sh, tid);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
+        sync_n<BAR>(nthr);
     }
     stamp(p, t, 7);
     if (warp == 0) {
@@ -451,7 +453,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
             }
         }
     }
-    sync_n(nthr);
+    sync_n<BAR>(nthr);
     {
         const double omega = sh.sc[0], N = sh.sc[2], aphi = sh.sc[5], bom = sh.sc[6];
         for (int idx = tid; idx < R * R; idx += nthr) {
@@ -472,8 +474,8 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
             sh.lam = (robust && (p.flags & F_FIXED_LAMBDA) == 0) ? lam + (double)p.d_global : lam;   // rPSMF.py:135
         }
     }
-    sync_n(nthr);
-    if (t + 1 < p.n_steps) predict_cta<R>(p, sh, tid, p.k0 + t + 1, series, nthr);
+    sync_n<BAR>(nthr);
+    if (t + 1 < p.n_steps) predict_cta<R, BAR>(p, sh, tid, p.k0 + t + 1, series, nthr);
 }
 
 // ---- cross-GPU exchange of the (already grid-reduced) statistics over NVLink -------------------------------
@@ -484,7 +486,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
 // world slots in rank order -- the same order on every GPU, so the replicated state stays bit-identical.
 // Two parities make the mailbox safe without a second handshake: a GPU can only be one step ahead of its
 // slowest peer (it needs that peer's flag of the current step to proceed).
-template <int NST, int NSP>
+template <int NST, int NSP, int BAR = 0>
 __device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restrict__ tot, double* __restrict__ tmp, int tid,
                                              int64_t t, int part, int nthr) {
     const int parity = (int)((p.step_base + (unsigned long long)t) & 1ULL);
@@ -496,7 +498,7 @@ __device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restric
                 if (pr != p.rank) st_relaxed_sys_f64(p.mbox_peer[pr] + ((size_t)parity * MAX_PEERS + p.rank) * NSP + e, v);
         }
         __threadfence_system();
-        sync_n(nthr);
+        sync_n<BAR>(nthr);
         if (tid < p.world && tid != p.rank)
             st_release_sys(p.flag_peer[tid] + parity * MAX_PEERS + p.rank, target);
     }
@@ -505,16 +507,16 @@ __device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restric
         while (ld_acquire_sys(f) < target) {
         }
     }
-    sync_n(nthr);
+    sync_n<BAR>(nthr);
     for (int e = tid; e < NST; e += nthr) {
         double s = 0.0;
         for (int src = 0; src < p.world; ++src)
             s += (src == p.rank) ? tot[e] : ld_relaxed_sys_f64(p.mbox_local + ((size_t)parity * MAX_PEERS + src) * NSP + e);
         tmp[e] = s;
     }
-    sync_n(nthr);
+    sync_n<BAR>(nthr);
     for (int e = tid; e < NST; e += nthr) tot[e] = tmp[e];
-    sync_n(nthr);
+    sync_n<BAR>(nthr);
 }
 
 // ---- cross-CTA reduction of the statistics, deterministic (fixed summation order) ---------------------
@@ -522,13 +524,13 @@ __device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restric
 //   cps  > 16 : reduce-scatter / all-gather through L2: CTA c sums entries {c, c + cps, ..} over all CTAs
 //               (coalesced reads of a transposed partial array), a second barrier publishes the totals.
 // sh.part -> sh.tot; ends with a barrier over the `nthr` threads.
-template <int NST, int NSP>
+template <int NST, int NSP, int BAR = 0>
 __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict__ part_v, double* __restrict__ tot, int tid,
                                             int lane, int warp, int64_t t, int series, int part, int nthr) {
     if (p.cps == 1) {
         for (int e = tid; e < NST; e += nthr) tot[e] = part_v[e];
-        sync_n(nthr);
-        if (p.world > 1) gpu_exchange<NST, NSP>(p, tot, part_v, tid, t, part, nthr);
+        sync_n<BAR>(nthr);
+        if (p.world > 1) gpu_exchange<NST, NSP, BAR>(p, tot, part_v, tid, t, part, nthr);
         return;
     }
     const int parity = (int)(t & 1);
@@ -537,7 +539,7 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
         double* mine = p.partials + ((size_t)parity * cps + part) * NSP;
         for (int e = tid; e < NST; e += nthr) mine[e] = part_v[e];
         stamp(p, t, 3);
-        grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), nthr);
+        grid_barrier<BAR>(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), nthr, tid);
         stamp(p, t, 4);
         const double* basep = p.partials + (size_t)parity * cps * NSP;
         for (int e = tid; e < NST; e += nthr) {
@@ -553,7 +555,7 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
         double* totals = pT + (size_t)NSP * pstr;
         for (int e = tid; e < NST; e += nthr) pT[(size_t)e * pstr + part] = part_v[e];
         stamp(p, t, 3);
-        grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 1), nthr);
+        grid_barrier<BAR>(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 1), nthr, tid);
         const int nw = nthr >> 5;
         for (int e = part + warp * cps; e < NST; e += nw * cps) {
             const double* src = pT + (size_t)e * pstr;
@@ -570,12 +572,12 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
             s = warp_allsum(s);
             if (lane == 0) totals[e] = s;
         }
-        grid_barrier(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 2), nthr);
+        grid_barrier<BAR>(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 2), nthr, tid);
         stamp(p, t, 4);
         for (int e = tid; e < NST; e += nthr) tot[e] = __ldcg(totals + e);
     }
-    sync_n(nthr);
-    if (p.world > 1) gpu_exchange<NST, NSP>(p, tot, part_v, tid, t, part, nthr);
+    sync_n<BAR>(nthr);
+    if (p.world > 1) gpu_exchange<NST, NSP, BAR>(p, tot, part_v, tid, t, part, nthr);
 }
 
 // ---- direct-load persistent kernel: C tiles are read from / written to global memory by the warp that

@@ -7,9 +7,10 @@
 //       1-D TMA path: UBLKCP in SASS) that complete on mbarriers, and bulk-stores updated chunks back.
 //       streaming (chunks of the CTA > slots): ring, every chunk loaded and stored once per step;
 //       resident  (chunks <= slots): C is loaded once, stays in shared memory for the whole launch.
-//   pass warps (12)  one warp per 32-row tile, all warps independent (psmf_filter.cuh: lane = row for the
+//   pass warps (12 / 9)  one warp per 32-row tile, all warps independent (psmf_filter.cuh: lane = row for the
 //       rank-1 update / y_hat / e, fp64 DMMA fragments for the Gram-type sums).
-//   control warps (3) CTA partial -> deterministic grid reduction (+ NVLink exchange) -> r x r solve.
+//   reducer warp (1)  CTA partial -> deterministic grid reduction (+ NVLink exchange) of step t+1, while the
+//   solver warps (2 / 5) run the r x r solve of step t.
 //
 // Software pipeline.  The statistics of step t are sums over C_t = C_{t-1} + e_{t-1} g_{t-1}', and g_{t-1}
 // only exists after the solve of step t-1.  Expanding the rank-1 term,
@@ -34,8 +35,11 @@
 namespace psmf {
 
 constexpr int MAXSLOT = 64;
-constexpr int V2_CTRL_WARPS = 3;                                   // reduction + r x r solve
-constexpr int V2_PASS_WARPS = V2_CWARPS - V2_CTRL_WARPS;           // 12: one tile takes a warp ~1.6 us
+// warp groups: warp 0 = reducer, warps 1..NSOLVE = solver, the next NPASS = V2_CWARPS - 1 - NSOLVE warps run
+// the row pass, the last warp is the producer.  Two configurations are instantiated:
+//   streaming (pass-bound):            NSOLVE = 2, 12 pass warps
+//   resident  (latency-bound, multi-GPU): NSOLVE = 5,  9 pass warps
+__host__ __device__ constexpr int s_npass(int NSOLVE) { return V2_CWARPS - 1 - NSOLVE; }
 
 __host__ __device__ constexpr int s_threads() { return (V2_CWARPS + 1) * 32; }
 
@@ -104,15 +108,17 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int R>
 struct PipeSmem {
     static constexpr int NSP2 = nstat2_pad(R);
-    double tot2[NSP2];
-    double part2[NSP2];
+    double tot2[2][NSP2];          // reduced sums of step t in tot2[t & 1]   (reducer -> solver)
+    double part2[NSP2];            // reducer scratch
+    double asm2[NSP2];             // solver scratch (assembled A_t, h_t)
     double par[2][2 * R];          // par[t & 1] = {g_t (R), xbar_{t+1} (R)} published by the solve of step t
     double xb0[R];                 // xbar_0 (from the state entering the launch)
     uint64_t full[MAXSLOT];        // slot loaded            (producer -> pass warps)
     uint64_t done[MAXSLOT];        // slot processed         (pass warps -> producer)
     uint64_t stats_full[2];        // partial sums of pass t written        (pass warps -> control)
     uint64_t red_free;             // partial sums consumed                  (control -> pass warps)
-    uint64_t par_full[2];          // par[t & 1] published                   (control -> pass warps)
+    uint64_t par_full[2];          // par[t & 1] published                   (solver -> pass warps)
+    uint64_t tot_full[2];          // tot2[t & 1] written                    (reducer -> solver)
 };
 
 // per-warp accumulators of one pipelined pass
@@ -155,7 +161,7 @@ __device__ __forceinline__ YM<T> load_ym(const KParams& p, const T* __restrict__
     return r;
 }
 
-template <int R, typename T, bool FLUSH>
+template <int R, typename T, bool FLUSH, int NPW>
 __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, double* __restrict__ ebuf,
                                             unsigned char* __restrict__ slots, double* __restrict__ red, T* __restrict__ Yrec_prev,
                                             const T* __restrict__ Yb, const uint8_t* __restrict__ Mb, int tb, int nt, int nslot,
@@ -174,10 +180,10 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
     long long wait_full = 0;
 
     YM<T> nx = load_ym<T>(p, Yb, Mb, pass, (int64_t)(tb + wp) * TILE + lane, has_prev, has_cur);
-    for (int tl = wp; tl < nt; tl += V2_PASS_WARPS) {
+    for (int tl = wp; tl < nt; tl += NPW) {
         const YM<T> ym = nx;
-        if (tl + V2_PASS_WARPS < nt)                                   // prefetch y / m of this warp's next tile
-            nx = load_ym<T>(p, Yb, Mb, pass, (int64_t)(tb + tl + V2_PASS_WARPS) * TILE + lane, has_prev, has_cur);
+        if (tl + NPW < nt)                                             // prefetch y / m of this warp's next tile
+            nx = load_ym<T>(p, Yb, Mb, pass, (int64_t)(tb + tl + NPW) * TILE + lane, has_prev, has_cur);
         const int k = tl / TS, i = tl - k * TS;
         const int64_t kk = pass * nchunks + k;
         const int slot = streaming ? (int)(kk % nslot) : k;
@@ -372,26 +378,25 @@ __device__ void s_producer(const KParams& p, PipeSmem<R>& ps, unsigned char* slo
     bulk_wait<0>();
 }
 
-// ---- control warps: pipelined sums of step t (+ g_{t-1}, xbar_t) -> statistics vector of psmf_filter.cuh ----
+// ---- solver warps: pipelined sums of step t (+ g_{t-1}, xbar_t) -> statistics vector of psmf_filter.cuh ----
 // sh.g = g_{t-1}, sh.xb = xbar_t, sh.w1/w0 for step t are current (left by the solve of step t-1).
-template <int R>
-__device__ __forceinline__ void assemble_stats(Smem<R>& sh, PipeSmem<R>& ps, int tid, int nthr) {
+template <int R, int BAR>
+__device__ __forceinline__ void assemble_stats(Smem<R>& sh, PipeSmem<R>& ps, const double* __restrict__ t2, int tid, int nthr) {
     constexpr int NGm = ngram(R);
-    const double* t2 = ps.tot2;
     const double kappa = t2[NGm + 2 * R + 0], psi = t2[NGm + 2 * R + 1], gamma = t2[NGm + 2 * R + 2];
     // A_t (packed upper triangle) -> part2[0..NGm), h_t -> part2[NGm..NGm+R)
     for (int idx = tid; idx < R * R; idx += nthr) {
         const int j = idx / R, k = idx % R;
         if (j <= k) {
             const double gj = sh.g[j], gk = sh.g[k];
-            ps.part2[gram_off(R, j) + (k - j)] = t2[gram_off(R, j) + (k - j)] + (t2[NGm + j] * gk + gj * t2[NGm + k]) + kappa * gj * gk;
+            ps.asm2[gram_off(R, j) + (k - j)] = t2[gram_off(R, j) + (k - j)] + (t2[NGm + j] * gk + gj * t2[NGm + k]) + kappa * gj * gk;
         }
     }
     if (tid >= nthr - R) {
         const int j = tid - (nthr - R);
-        ps.part2[NGm + j] = fma(psi, sh.g[j], t2[NGm + R + j]);
+        ps.asm2[NGm + j] = fma(psi, sh.g[j], t2[NGm + R + j]);
     }
-    sync_n(nthr);
+    sync_n<BAR>(nthr);
     // bu = h - A xbar ; q1 = gamma - 2 xbar'h + xbar'A xbar   (warp 0)
     if (tid < 32) {
         const int lane = tid;
@@ -401,14 +406,14 @@ __device__ __forceinline__ void assemble_stats(Smem<R>& sh, PipeSmem<R>& ps, int
 #pragma unroll
             for (int k = 0; k < R; k += 2) {
                 const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
-                a0 = fma(ps.part2[gram_off(R, lo) + hi - lo], sh.xb[k], a0);
+                a0 = fma(ps.asm2[gram_off(R, lo) + hi - lo], sh.xb[k], a0);
                 if (k + 1 < R) {
                     const int lo1 = k + 1 < lane ? k + 1 : lane, hi1 = k + 1 < lane ? lane : k + 1;
-                    a1 = fma(ps.part2[gram_off(R, lo1) + hi1 - lo1], sh.xb[k + 1], a1);
+                    a1 = fma(ps.asm2[gram_off(R, lo1) + hi1 - lo1], sh.xb[k + 1], a1);
                 }
             }
             ax = a0 + a1;
-            hj = ps.part2[NGm + lane];
+            hj = ps.asm2[NGm + lane];
             xj = sh.xb[lane];
         }
         const double xh = warp_allsum(xj * hj);
@@ -426,17 +431,18 @@ __device__ __forceinline__ void assemble_stats(Smem<R>& sh, PipeSmem<R>& ps, int
     }
     {
         const double w1 = sh.w1;
-        for (int idx = tid; idx < NGm; idx += nthr) sh.tot[idx] = w1 * ps.part2[idx];   // G = w1 A_t
+        for (int idx = tid; idx < NGm; idx += nthr) sh.tot[idx] = w1 * ps.asm2[idx];   // G = w1 A_t
     }
-    sync_n(nthr);
+    sync_n<BAR>(nthr);
 }
 
-template <int R, typename T>
+template <int R, typename T, int NSOLVE>
 __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KParams p) {
     using L = SlotLayout<R, T>;
     constexpr int NSP2 = nstat2_pad(R), NST2 = nstat2(R);
-    constexpr int NCT = V2_CTRL_WARPS * 32;                     // control threads = tid 0..191
-    constexpr int NPW = V2_PASS_WARPS;
+    constexpr int NPW = s_npass(NSOLVE);
+    constexpr int NSV = NSOLVE * 32;                            // solver threads
+    constexpr int BAR_RED = 0, BAR_GJ = 1, BAR_XB0 = 2, BAR_SOLVE = 3;
     extern __shared__ __align__(128) unsigned char dyn_smem_s[];
     __shared__ Smem<R> sh;
     __shared__ __align__(8) PipeSmem<R> ps;
@@ -467,6 +473,8 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
         mbar_init(&ps.red_free, 1);
         mbar_init(&ps.par_full[0], 1);
         mbar_init(&ps.par_full[1], 1);
+        mbar_init(&ps.tot_full[0], 1);
+        mbar_init(&ps.tot_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < R * R; i += blockDim.x) {
@@ -492,49 +500,64 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
         return;
     }
 
-    if (warp < V2_CTRL_WARPS) {
-        // ---- control warps: reduce + solve of step t while the pass warps run pass t+1 ----
-        predict_cta<R>(p, sh, tid, p.k0, series, NCT);                 // xbar_0, Pbar_0, a_0, w1/w0
-        if (tid < R) ps.xb0[tid] = sh.xb[tid];
-        __threadfence_block();
-        asm volatile("bar.arrive 2, %0;" ::"r"(NCT + NPW * 32) : "memory");     // xbar_0 is published
+    if (warp == 0) {
+        // ---- reducer warp: partial sums of pass t -> grid (and GPU) totals of step t ----
         for (int64_t t = 0; t < n; ++t) {
             stamp(p, t, 0);
             mbar_wait(&ps.stats_full[t & 1], (uint32_t)((t >> 1) & 1));
             stamp(p, t, 1);
-            for (int e = tid; e < NST2; e += NCT) {                     // CTA partial: fixed order over the pass warps
+            for (int e = lane; e < NST2; e += 32) {                     // CTA partial: fixed order over the pass warps
                 double s = 0.0;
 #pragma unroll
                 for (int w = 0; w < NPW; ++w) s += sh.red[w * NSP2 + e];
                 ps.part2[e] = s;
             }
-            sync_n(NCT);
-            if (tid == 0) mbar_arrive(&ps.red_free);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ps.red_free);
             stamp(p, t, 2);
-            grid_reduce<NST2, NSP2>(p, ps.part2, ps.tot2, tid, lane, warp, t, series, part, NCT);
+            // tot2[t & 1] was last read by the solve of step t-2, which completed before pass t could start
+            grid_reduce<NST2, NSP2, BAR_RED>(p, ps.part2, ps.tot2[t & 1], lane, lane, 0, t, series, part, 32);
+            __threadfence_block();
+            if (lane == 0) mbar_arrive(&ps.tot_full[t & 1]);
             stamp(p, t, 5);
-            assemble_stats<R>(sh, ps, tid, NCT);
-            small_update<R, NCT>(p, sh, tid, lane, warp, series, t, writer, NCT);
-            // publish g_t and xbar_{t+1} for pass t+2 (small_update ended with a barrier over the control threads)
-            if (tid < R) {
-                ps.par[t & 1][tid] = sh.g[tid];
-                ps.par[t & 1][R + tid] = sh.xb[tid];
+        }
+        return;
+    }
+
+    if (warp <= NSOLVE) {
+        // ---- solver warps: r x r solve of step t (needs the totals of step t and the solve of step t-1) ----
+        const int st = tid - 32, swarp = warp - 1;
+        predict_cta<R, BAR_SOLVE>(p, sh, st, p.k0, series, NSV);       // xbar_0, Pbar_0, a_0, w1/w0
+        if (st < R) ps.xb0[st] = sh.xb[st];
+        __threadfence_block();
+        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_XB0), "r"(NSV + NPW * 32) : "memory");     // xbar_0 is published
+        for (int64_t t = 0; t < n; ++t) {
+            mbar_wait(&ps.tot_full[t & 1], (uint32_t)((t >> 1) & 1));
+            if (st == 0) stamp_pass(p, t, 12, 0, true);
+            assemble_stats<R, BAR_SOLVE>(sh, ps, ps.tot2[t & 1], st, NSV);
+            small_update<R, NSV, BAR_SOLVE, BAR_GJ>(p, sh, st, lane, swarp, series, t, writer, NSV);
+            // publish g_t and xbar_{t+1} for pass t+2 (small_update ended with a barrier over the solver threads)
+            if (st < R) {
+                ps.par[t & 1][st] = sh.g[st];
+                ps.par[t & 1][R + st] = sh.xb[st];
             }
-            sync_n(NCT);
-            if (tid == 0) mbar_arrive(&ps.par_full[t & 1]);
-            stamp(p, t, 6);
+            sync_n<BAR_SOLVE>(NSV);
+            if (st == 0) {
+                mbar_arrive(&ps.par_full[t & 1]);
+                stamp_pass(p, t, 13, 0, true);
+            }
         }
         if (writer) {
-            for (int i = tid; i < R * R; i += NCT) {
+            for (int i = st; i < R * R; i += NSV) {
                 stg[st_P(R) + i] = sh.P[i];
                 stg[st_V(R) + i] = sh.V[i];
                 stg[st_Q(R) + i] = sh.Q[i];
             }
-            if (tid < R) {
-                stg[st_x(R) + tid] = sh.x[tid];
-                if (p.grad_out != nullptr) p.grad_out[(int64_t)series * R + tid] = sh.grad[tid];
+            if (st < R) {
+                stg[st_x(R) + st] = sh.x[st];
+                if (p.grad_out != nullptr) p.grad_out[(int64_t)series * R + st] = sh.grad[st];
             }
-            if (tid == 0) {
+            if (st == 0) {
                 stg[st_rho(R)] = sh.rho;
                 stg[st_lam(R)] = sh.lam;
             }
@@ -543,17 +566,17 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     }
 
     // ---- pass warps ----
-    const int wp = warp - V2_CTRL_WARPS;
+    const int wp = warp - 1 - NSOLVE;
     const T* Yb = reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst;
     const uint8_t* Mb = p.M != nullptr ? p.M + (int64_t)series * p.msst : nullptr;
-    asm volatile("bar.sync 2, %0;" ::"r"(NCT + NPW * 32) : "memory");   // xbar_0 available
+    asm volatile("bar.sync %0, %1;" ::"n"(BAR_XB0), "r"(NSV + NPW * 32) : "memory");   // xbar_0 available
     for (int64_t pass = 0; pass < n; ++pass) {
         // pass `pass` needs the solve of step pass-2 (g_{pass-2}, xbar_{pass-1})
         if (wp == 0 && lane == 0) stamp_pass(p, pass, 11, 0, true);
         if (pass >= 2) mbar_wait(&ps.par_full[(pass - 2) & 1], (uint32_t)(((pass - 2) >> 1) & 1));
         if (wp == 0 && lane == 0) stamp_pass(p, pass, 8, 0, true);
         T* Yrec_prev = (p.Yrec && pass >= 1) ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + (pass - 1) * p.ldrec : nullptr;
-        s_warp_pass<R, T, false>(p, ps, ebuf, slots, sh.red, Yrec_prev, Yb, Mb, tb, nt, nslot, pass, wp, lane);
+        s_warp_pass<R, T, false, NPW>(p, ps, ebuf, slots, sh.red, Yrec_prev, Yb, Mb, tb, nt, nslot, pass, wp, lane);
         if (wp == 0 && lane == 0) stamp_pass(p, pass, 9, 0, true);
     }
     // flush: both pending rank-1 updates -> C_n; needs the solves of steps n-2 and n-1
@@ -561,7 +584,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     mbar_wait(&ps.par_full[(n - 1) & 1], (uint32_t)(((n - 1) >> 1) & 1));
     {
         T* Yrec_prev = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + (n - 1) * p.ldrec : nullptr;
-        s_warp_pass<R, T, true>(p, ps, ebuf, slots, sh.red, Yrec_prev, Yb, Mb, tb, nt, nslot, n, wp, lane);
+        s_warp_pass<R, T, true, NPW>(p, ps, ebuf, slots, sh.red, Yrec_prev, Yb, Mb, tb, nt, nslot, n, wp, lane);
     }
 }
 

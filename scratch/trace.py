@@ -12,17 +12,14 @@ eng.set_state(C_=C0, V=init["V"], P=init["P"], x=x0, Q=init["Q"], rho=[init["rho
 tr = eng.set_trace(T)
 eng.run(Y, M, want_X=False); eng.run(Y, M, want_X=False)
 print(eng.status(), eng.launch_info())
-t = tr.cpu().numpy().astype(np.int64)
-t = t[20:]
-names = ["pass", "cta_sync", "part", "grid_bar", "tot", "gj", "rest_small", "next"]
-# stamps: 0 pass start,1 pass end,2 after sync,3 before bar,4 after bar,5 tot done,7 after GJ,6 step end
-seq = [0, 1, 2, 3, 4, 5, 7, 6]
-dts = np.stack([t[:, seq[i + 1]] - t[:, seq[i]] for i in range(7)], 1)
-step = t[1:, 0] - t[:-1, 0]
-print("d=%d kernel=%d  step mean %.2f us" % (d, kernel, step.mean() / 1e3))
-for n, v in zip(["pass", "cta_sync", "partials", "grid_barrier", "tot_reduce", "gauss_jordan", "small_rest"], dts.mean(0)):
-    print("  %-14s %8.2f us" % (n, v / 1e3))
-
+t = tr.cpu().numpy().astype(np.int64)[20:]
+us = lambda a: a.mean() / 1e3
+print("d=%d kernel=%d  step mean %.2f us" % (d, kernel, us(t[1:, 0] - t[:-1, 0])))
 if kernel == 2:
-    pw = t[:, 9] - t[:, 8]; pwait = t[:, 8] - t[:, 11]; wf = t[:, 10]
-    print("  pass warp 0: pass %.2f us, wait for solve(t-2) %.2f us, cycles waiting for slots %.0f (%.2f us @1.9GHz)" % (pw.mean()/1e3, pwait.mean()/1e3, wf.mean(), wf.mean()/1.9e3))
+    print("  reducer: wait for pass %.2f | CTA partial %.2f | grid barrier(s)+reduce %.2f (first barrier %.2f)"
+          % (us(t[:, 1] - t[:, 0]), us(t[:, 2] - t[:, 1]), us(t[:, 5] - t[:, 2]), us(t[:, 4] - t[:, 3])))
+    print("  solver : solve %.2f | idle before it %.2f" % (us(t[:, 13] - t[:, 12]), us(t[1:, 12] - t[:-1, 13])))
+    print("  pass warp 0: pass %.2f us, wait for solve(t-2) %.2f us, waiting for slots %.2f us"
+          % (us(t[:, 9] - t[:, 8]), us(t[:, 8] - t[:, 11]), t[:, 10].mean() / 1.9e3))
+else:
+    print("  pass %.2f | partial+barrier+reduce %.2f | solve %.2f" % (us(t[:, 1] - t[:, 0]), us(t[:, 5] - t[:, 1]), us(t[:, 6] - t[:, 5])))
