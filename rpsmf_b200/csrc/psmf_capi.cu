@@ -71,6 +71,7 @@ struct psmf_engine {
     double* state = nullptr;
     double* partials = nullptr;
     unsigned long long* bar = nullptr;
+    double* gparams = nullptr;
     long long* status = nullptr;
     int cps = 1, threads = 0, launches_last = 0, num_sms = 0;
     size_t dyn_smem = 0;
@@ -120,6 +121,7 @@ static void free_engine(psmf_engine* e) {
     cudaFree(e->state);
     cudaFree(e->partials);
     cudaFree(e->bar);
+    cudaFree(e->gparams);
     cudaFree(e->status);
     for (int i = 0; i < PSMF_MAX_PEERS; ++i)
         if (e->peer_mbox[i] && i != e->cfg.rank) cudaIpcCloseMemHandle(e->peer_mbox[i]);
@@ -192,19 +194,20 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     e->cooperative = cps > 1;
 
     // ---- TMA-staged kernel: slots of V2_TS tiles + y/m slices, residual buffer behind them ----
-    if (cfg->kernel != 1 && e->d % 16 == 0) {
+    if (cfg->kernel != 1 && e->d % 16 == 0 && e->S == 1 && sms >= 2) {
         const int TS = V2_TS;
         auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
         const size_t slot = r128((size_t)TS * e->R * TILE * e->esize);     // psmf_stream.cuh SlotLayout: one chunk of C
+        // data CTAs (one per SM) + one control CTA, all co-resident (cooperative launch)
         int cps2;
-        if (e->S > 1) cps2 = 1;
-        else if (cfg->ctas > 0) cps2 = cfg->ctas;
+        if (cfg->ctas > 0) cps2 = cfg->ctas;
         else {
-            int64_t want = e->ntiles / (V2_CWARPS + 1);                 // about one tile per consumer warp and step
-            cps2 = (int)(want < 1 ? 1 : (want > sms ? sms : want));
+            int64_t want = e->ntiles / V2_CWARPS;                       // about one tile per pass warp and step
+            cps2 = (int)(want < 1 ? 1 : want);
         }
         if ((int64_t)cps2 > e->ntiles) cps2 = (int)e->ntiles;
-        if (e->S == 1 && cps2 > sms) cps2 = sms;                       // one CTA per SM (cooperative launch)
+        if (cps2 > sms - 1) cps2 = sms - 1;
+        if (cps2 > 256) cps2 = 256;                                    // control CTA sums <= 256 CTA partials per entry
         LaunchShape shp2;
         if (SHAPE_S[e->R](cfg->dtype, 0, &shp2) == cudaSuccess) {
             const int64_t tiles_max = (e->ntiles + cps2 - 1) / cps2;
@@ -252,9 +255,10 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     {
         const int cmax = e->cps > e->cps2 ? e->cps : e->cps2;
         const size_t pstr = (size_t)((cmax + 7) & ~7) + 1;            // transposed partials + totals (grid_reduce)
-        CKC(cudaMalloc(&e->partials, (size_t)2 * nsp * (pstr > 17 ? pstr : 17) * sizeof(double)));
+        CKC(cudaMalloc(&e->partials, (size_t)2 * nsp * (pstr > 17 ? pstr : 17) * sizeof(double)));   // also >= 2 * cps2 * nstat2_pad
     }
-    CKC(cudaMalloc(&e->bar, sizeof(unsigned long long)));
+    CKC(cudaMalloc(&e->bar, 8 * sizeof(unsigned long long)));
+    CKC(cudaMalloc(&e->gparams, 4 * MAXR * 16));                        // [2][2R] 16-byte cells (psmf_stream.cuh)
     CKC(cudaMalloc(&e->status, sizeof(long long)));
     CKC(cudaMemset(e->status, 0xFF, sizeof(long long)));
     if (cfg->world_size > 1) {
@@ -372,7 +376,8 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
         p.step_base = h->step_base;
     }
     p.trace = h->trace; p.trace_steps = h->trace_steps;
-    CK(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned long long), st));
+    CK(h, cudaMemsetAsync(h->bar, 0, 8 * sizeof(unsigned long long), st));
+    CK(h, cudaMemsetAsync(h->gparams, 0, 4 * MAXR * 16, st));
     CK(h, cudaMemsetAsync(h->status, 0xFF, sizeof(long long), st));
     // the TMA-staged kernel needs 16-byte aligned rows of Y / M (bulk copies)
     const size_t es = h->esize;
@@ -386,8 +391,13 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     if (use2) {
         p.cps = h->cps2;
         p.nslot = h->nslot;
-        p.nsolve = h->resident2 ? 5 : 2;
-        CK(h, LAUNCH_S[h->R](p, h->cfg.dtype, h->S * h->cps2, h->dyn_smem2, st, h->cps2 > 1));
+        p.trace_cta = h->cps2;
+        // streaming from HBM: fewer pass warps keep up with the ring and leave issue slots to the producer (measured
+        // optimum 11 of 15 at r = 16); resident in shared memory: every warp helps
+        p.npw = h->resident2 ? V2_CWARPS : (V2_CWARPS * 3 + 3) / 4;
+        if (const char* ev = getenv("PSMF_NPW")) { const int v = atoi(ev); if (v >= 1 && v <= V2_CWARPS) p.npw = v; }
+        p.gparams = h->gparams;
+        CK(h, LAUNCH_S[h->R](p, h->cfg.dtype, h->cps2 + 1, h->dyn_smem2, st, true));
         h->last_kernel = 2;
     } else {
         CK(h, LAUNCH[h->R](p, h->cfg.dtype, h->S * h->cps, h->dyn_smem, st, h->cooperative));
@@ -412,7 +422,7 @@ extern "C" int psmf_status(psmf_handle h, int64_t* first_bad_step) {
 extern "C" int psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* smem_bytes, int32_t* launches) {
     if (!h) return PSMF_E_INVALID;
     const bool k2 = h->last_kernel == 2;
-    if (ctas) *ctas = k2 ? h->cps2 : h->cps;
+    if (ctas) *ctas = k2 ? h->cps2 + 1 : h->cps;
     if (threads) *threads = k2 ? h->threads2 : h->threads;
     if (smem_bytes) *smem_bytes = (int32_t)(k2 ? h->dyn_smem2 : h->dyn_smem);
     if (launches) *launches = h->launches_last;

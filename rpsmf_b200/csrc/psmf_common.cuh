@@ -68,8 +68,8 @@ struct KParams {
     double* scal_out;
     const double* xbar_ext; const double* F_ext;
     double* grad_out;         // (n_series, R) accumulated theta gradient or nullptr
-    double* partials;         // [2][ctas][nstat_pad]
-    unsigned long long* bar;  // grid barrier counter (monotonic within a launch)
+    double* partials;         // direct kernel: grid_reduce scratch; pipelined kernel: [2][cps][nstat2_pad]
+    unsigned long long* bar;  // direct kernel: grid barrier counter; pipelined kernel: [0..1] arrival counters, [2] flag
     long long* status;        // first bad step or -1
     int64_t d, d_global;
     int64_t n_steps, k0;
@@ -85,7 +85,9 @@ struct KParams {
     unsigned long long step_base;
     // streaming kernel
     int32_t nslot;            // shared-memory chunk slots per CTA
-    int32_t nsolve;           // solver warps of the pipelined kernel (2: streaming, 5: resident)
+    int32_t npw;              // pipelined kernel: active pass warps per data CTA
+    int32_t trace_cta;        // CTA whose thread 0 writes the control stamps (0: direct kernel, cps: control CTA)
+    double* gparams;          // pipelined kernel: [2][2 * MAXR] parameter sets published by the control CTA
     int32_t trace_steps;      // debug: number of steps recorded in `trace`
     unsigned long long* trace; // debug: [trace_steps][8] globaltimer stamps of CTA 0 (or nullptr)
 };

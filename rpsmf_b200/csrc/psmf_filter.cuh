@@ -40,7 +40,6 @@ struct Smem {
     double aug[2][R][2 * R + 2];   // double-buffered augmented matrix of the r x r solve
     double tot[NSP];
     double part[NSP];
-    double red[MAXW * nstat2_pad(R)];   // per-warp partial statistics (sized for the pipelined kernel's vector)
     double a, rho, lam;
     double w1, w0;                 // 1/(rho + a), 1/a : the only two values of w_i (rPSMF.py:92,98,32)
     double sc[8];                  // omega, eta, N, phi, sSe, alpha*phi, beta*omega
@@ -94,12 +93,13 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
 }
 
 // debug phase stamps (CTA 0, thread 0): enabled when KParams.trace != nullptr
-__device__ __forceinline__ void stamp(const KParams& p, int64_t t, int slot) {
-    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && t < p.trace_steps) {
+__device__ __forceinline__ void stamp(const KParams& p, int64_t t, int slot, int who = 0) {
+    if (p.trace != nullptr && blockIdx.x == p.trace_cta && threadIdx.x == who && t < p.trace_steps) {
         unsigned long long v;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
         p.trace[t * 16 + slot] = v;
     }
+    __syncwarp();   // the single-thread branch above must not leave the warp split (shuffles would take the slow path)
 }
 
 // debug stamps of the first pass warp (psmf_stream.cuh): slot 8.. of the 16-entry trace row
@@ -111,6 +111,7 @@ __device__ __forceinline__ void stamp_pass(const KParams& p, int64_t t, int slot
 }
 
 __device__ __forceinline__ double warp_allsum(double v) {
+    __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;   // bit-identical on every lane (a+b == b+a at every stage)
@@ -306,9 +307,8 @@ __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, i
 // integer max over the high words of |a_ik| (16 mantissa bits decide, ties -> lowest row) -- and perm[k]
 // remembers it, so the solution row of unknown k is aug[R & 1][perm[k]].
 constexpr int GJ_THREADS = 192;                         // direct-load kernel; the pipelined kernel uses its control warps
-template <int R, int NGJ, int GJBAR = 1>
+template <int R, int NGJ, int GJBAR = 1, int NC = 2 * R + 1>
 __device__ void gauss_jordan_cta(Smem<R>& sh, int tid) {
-    constexpr int NC = 2 * R + 1;
     constexpr int TPR = NGJ / R;                        // threads per row
     constexpr int CPT = (NC + TPR - 1) / TPR;           // columns per thread
     const bool active = tid < R * TPR;
@@ -587,6 +587,7 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
     constexpr int NW = V1_WARPS, NSP = nstat_pad(R), NST = nstat(R);
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ Smem<R> sh;
+    __shared__ double red[V1_WARPS * nstat_pad(R)];                            // per-warp partial statistics
     double* stage_all = reinterpret_cast<double*>(dyn_smem);                   // NW staging tiles [R][32] fp64
     double* ebuf = stage_all + NW * R * TILE;
 
@@ -655,14 +656,14 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
             tile_gram<R, double>(acc, stage, mbits, lane);
             __syncwarp();
         }
-        acc_writeout<R>(acc, sh.red + warp * NSP, w1, lane);
+        acc_writeout<R>(acc, red + warp * NSP, w1, lane);
         stamp(p, t, 1);
         __syncthreads();
         stamp(p, t, 2);
         if (tid < NST) {                                   // CTA partial: fixed order over the warps
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) s += sh.red[w * NSP + tid];
+            for (int w = 0; w < NW; ++w) s += red[w * NSP + tid];
             sh.part[tid] = s;
         }
         grid_reduce<NST, NSP>(p, sh.part, sh.tot, tid, lane, warp, t, series, part, blockDim.x);

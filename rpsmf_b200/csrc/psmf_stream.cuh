@@ -1,16 +1,21 @@
 // TMA-staged, software-pipelined PSMF / rPSMF filter kernel (sm_100a): the large-d path.
 //
-// Three warp groups per CTA (one CTA per SM, cooperative launch):
+// One cooperative launch of (data CTAs + 1 control CTA), one CTA per SM:
 //
-//   producer (1 warp, one thread)  moves contiguous CHUNKS of the tiled C (plus the matching slices of y and
-//       m) between HBM and a ring of shared-memory slots with bulk asynchronous copies (cp.async.bulk, the
-//       1-D TMA path: UBLKCP in SASS) that complete on mbarriers, and bulk-stores updated chunks back.
-//       streaming (chunks of the CTA > slots): ring, every chunk loaded and stored once per step;
-//       resident  (chunks <= slots): C is loaded once, stays in shared memory for the whole launch.
-//   pass warps (12 / 9)  one warp per 32-row tile, all warps independent (psmf_filter.cuh: lane = row for the
-//       rank-1 update / y_hat / e, fp64 DMMA fragments for the Gram-type sums).
-//   reducer warp (1)  CTA partial -> deterministic grid reduction (+ NVLink exchange) of step t+1, while the
-//   solver warps (2 / 5) run the r x r solve of step t.
+//   data CTA     producer warp (one thread): moves contiguous CHUNKS of the tiled C between HBM and a ring of
+//                shared-memory slots with bulk asynchronous copies (cp.async.bulk, the 1-D TMA path: UBLKCP in
+//                SASS) that complete on mbarriers, and bulk-stores updated chunks back.
+//                   streaming (chunks of the CTA > slots): ring, every chunk loaded and stored once per step;
+//                   resident  (chunks <= slots): C is loaded once and stays in shared memory for the launch.
+//                15 pass warps: one warp per 32-row tile, all warps independent (lane = row for the rank-1
+//                update / y_hat / e, fp64 DMMA fragments for the Gram-type sums); the last warp to finish a pass
+//                adds the 15 per-warp partials in fixed order, writes the CTA partial to global memory and
+//                bumps a global arrival counter.
+//   control CTA  waits for the arrival counter, adds the CTA partials in fixed order (deterministic), exchanges
+//                with the other GPUs over NVLink, runs the r x r solve with all its threads and publishes
+//                {g_t, xbar_{t+1}} + a flag in global memory.  It is the only CTA that holds V, P, Q, x, lambda.
+//                A dedicated SM keeps the latency-bound solve away from the DMMA traffic of the pass warps
+//                (measured: 3 us alone vs 8-23 us when it shared an SM with them) and removes every grid barrier.
 //
 // Software pipeline.  The statistics of step t are sums over C_t = C_{t-1} + e_{t-1} g_{t-1}', and g_{t-1}
 // only exists after the solve of step t-1.  Expanding the rank-1 term,
@@ -27,19 +32,19 @@
 // step time becomes max(pass, (pass + reduce + solve) / 2) instead of pass + reduce + solve.  One extra
 // read of y_t / m_t per step (+3 % HBM bytes) pays for it; C is still read and written once per step.
 //
-// Requirements checked by the host (else the direct-load kernel of psmf_filter.cuh is used): 16-byte
-// aligned Y / M base pointers and time strides, d a multiple of 16.
+// Parameter sets: set s = {g_{s-1}, xbar_s} (set 0 = {0, xbar_0} from the state entering the launch); pass p
+// needs set p-1, the flush pass n needs sets n-1 and n.  The control CTA publishes set t+1 after the solve
+// of step t at gparams[(t+1) & 1] and then stores flag = t+2.
+//
+// Requirements checked by the host (else the direct-load kernel of psmf_filter.cuh is used): one series,
+// d a multiple of 16, at least two SMs.
 #pragma once
 #include "psmf_filter.cuh"
 
 namespace psmf {
 
 constexpr int MAXSLOT = 64;
-// warp groups: warp 0 = reducer, warps 1..NSOLVE = solver, the next NPASS = V2_CWARPS - 1 - NSOLVE warps run
-// the row pass, the last warp is the producer.  Two configurations are instantiated:
-//   streaming (pass-bound):            NSOLVE = 2, 12 pass warps
-//   resident  (latency-bound, multi-GPU): NSOLVE = 5,  9 pass warps
-__host__ __device__ constexpr int s_npass(int NSOLVE) { return V2_CWARPS - 1 - NSOLVE; }
+constexpr int V2_PASS_WARPS = V2_CWARPS;                           // 15 pass warps + 1 producer warp per data CTA
 
 __host__ __device__ constexpr int s_threads() { return (V2_CWARPS + 1) * 32; }
 
@@ -104,21 +109,17 @@ __device__ __forceinline__ void bulk_wait() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// shared state of the pipeline (in addition to Smem<R>)
+// shared state of a data CTA
 template <int R>
-struct PipeSmem {
+struct DataSmem {
     static constexpr int NSP2 = nstat2_pad(R);
-    double tot2[2][NSP2];          // reduced sums of step t in tot2[t & 1]   (reducer -> solver)
-    double part2[NSP2];            // reducer scratch
-    double asm2[NSP2];             // solver scratch (assembled A_t, h_t)
-    double par[2][2 * R];          // par[t & 1] = {g_t (R), xbar_{t+1} (R)} published by the solve of step t
-    double xb0[R];                 // xbar_0 (from the state entering the launch)
+    double par[2][2 * R];          // par[s & 1] = parameter set s = {g_{s-1} (R), xbar_s (R)}
+    double red[V2_PASS_WARPS * NSP2];   // per-warp partial sums of the current pass
     uint64_t full[MAXSLOT];        // slot loaded            (producer -> pass warps)
     uint64_t done[MAXSLOT];        // slot processed         (pass warps -> producer)
-    uint64_t stats_full[2];        // partial sums of pass t written        (pass warps -> control)
-    uint64_t red_free;             // partial sums consumed                  (control -> pass warps)
-    uint64_t par_full[2];          // par[t & 1] published                   (solver -> pass warps)
-    uint64_t tot_full[2];          // tot2[t & 1] written                    (reducer -> solver)
+    uint64_t par_full[2];          // par[s & 1] copied from global memory   (pass warp 0 -> pass warps)
+    volatile int arrived;          // pass warps that have written their partial (monotonic over the launch)
+    volatile int sum_done;         // passes whose CTA partial has been written to global memory
 };
 
 // per-warp accumulators of one pipelined pass
@@ -161,19 +162,19 @@ __device__ __forceinline__ YM<T> load_ym(const KParams& p, const T* __restrict__
     return r;
 }
 
-template <int R, typename T, bool FLUSH, int NPW>
-__device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, double* __restrict__ ebuf,
-                                            unsigned char* __restrict__ slots, double* __restrict__ red, T* __restrict__ Yrec_prev,
+template <int R, typename T, bool FLUSH>
+__device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, double* __restrict__ ebuf,
+                                            unsigned char* __restrict__ slots, T* __restrict__ Yrec_prev,
                                             const T* __restrict__ Yb, const uint8_t* __restrict__ Mb, int tb, int nt, int nslot,
-                                            int64_t pass, int wp, int lane) {
+                                            int64_t pass, int wp, int lane, int NPW) {
     using L = SlotLayout<R, T>;
     constexpr int TS = L::TS, NSP2 = nstat2_pad(R);
     const int nchunks = (nt + TS - 1) / TS;
     const bool streaming = nchunks > nslot;
-    // g_{pass-2} and xbar_{pass-1} were published by the solve of step pass-2
-    const double* gp = (pass >= 2) ? ps.par[(pass - 2) & 1] : ps.xb0;
-    const double* xbp = (pass >= 2) ? ps.par[(pass - 2) & 1] + R : ps.xb0;
-    const double* gl = ps.par[(pass - 1) & 1];                          // g_{n-1} (flush only)
+    // parameter set pass-1 = {g_{pass-2}, xbar_{pass-1}}; the flush pass also needs g_{n-1} from set n
+    const double* gp = ps.par[(pass - 1) & 1];
+    const double* xbp = ps.par[(pass - 1) & 1] + R;
+    const double* gl = ps.par[pass & 1];
     const bool has_prev = pass >= 1, has_cur = !FLUSH;
     PassAcc acc;
     acc.zero();
@@ -276,9 +277,10 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
     }
     if constexpr (!FLUSH) {
         if (wp == 0 && lane == 0) stamp_pass(p, pass, 10, (unsigned long long)wait_full, false);
-        // the control warps have consumed the partial sums of the previous pass
-        if (pass >= 1) mbar_wait(&ps.red_free, (uint32_t)((pass - 1) & 1));
-        double* r0 = red + wp * NSP2;
+        // the CTA partial of the previous pass has left the per-warp buffers
+        while (ps.sum_done < (int)pass) {
+        }
+        double* r0 = ps.red + wp * NSP2;
         const int kq = lane & 3, mm = lane >> 2;
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
@@ -305,7 +307,33 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
         bfly<5, 16, 5>(acc.v, lane, base, lim);
         if (base < lim) r0[ngram(R) + 2 * R + base] = acc.v[0];
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ps.stats_full[pass & 1]);
+        // the last warp to arrive adds the per-warp partials in fixed warp order, writes the CTA partial to
+        // global memory and bumps the arrival counter the control CTA is waiting on
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            last = (atomicAdd((int*)&ps.arrived, 1) == (int)(pass + 1) * NPW - 1) ? 1 : 0;
+        }
+        last = __shfl_sync(FULL, last, 0);
+        if (last) {
+            __threadfence_block();
+            constexpr int NST2 = nstat2(R);
+            // transposed layout [parity][entry][cta]: the control CTA reads one entry of all CTAs coalesced
+            const int pstr = (p.cps + 7) & ~7;
+            double* gpart = p.partials + (size_t)(pass & 1) * NSP2 * pstr + blockIdx.x;
+            for (int e = lane; e < NST2; e += 32) {
+                double sum = 0.0;
+                for (int w = 0; w < NPW; ++w) sum += ps.red[w * NSP2 + e];
+                gpart[(size_t)e * pstr] = sum;
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                red_release_gpu(p.bar + (pass & 1), 1ULL);
+                ps.sum_done = (int)pass + 1;
+                __threadfence_block();
+            }
+        }
     }
 }
 
@@ -313,7 +341,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, PipeSmem<R>& ps, d
 // The loop is latency-bound per iteration (~0.6 us measured, scratch/bulkbench.cu): one bulk store and one
 // bulk load of a 16 KB chunk per iteration is what sustains the HBM rate, so nothing else goes through it.
 template <int R, typename T>
-__device__ void s_producer(const KParams& p, PipeSmem<R>& ps, unsigned char* slots, T* Cs, int tb, int nt, int nslot) {
+__device__ void s_producer(const KParams& p, DataSmem<R>& ps, unsigned char* slots, T* Cs, int tb, int nt, int nslot) {
     using L = SlotLayout<R, T>;
     constexpr int TS = L::TS;
     const int nchunks = (nt + TS - 1) / TS;
@@ -378,106 +406,126 @@ __device__ void s_producer(const KParams& p, PipeSmem<R>& ps, unsigned char* slo
     bulk_wait<0>();
 }
 
-// ---- solver warps: pipelined sums of step t (+ g_{t-1}, xbar_t) -> statistics vector of psmf_filter.cuh ----
-// sh.g = g_{t-1}, sh.xb = xbar_t, sh.w1/w0 for step t are current (left by the solve of step t-1).
-template <int R, int BAR>
-__device__ __forceinline__ void assemble_stats(Smem<R>& sh, PipeSmem<R>& ps, const double* __restrict__ t2, int tid, int nthr) {
-    constexpr int NGm = ngram(R);
-    const double kappa = t2[NGm + 2 * R + 0], psi = t2[NGm + 2 * R + 1], gamma = t2[NGm + 2 * R + 2];
-    // A_t (packed upper triangle) -> part2[0..NGm), h_t -> part2[NGm..NGm+R)
-    for (int idx = tid; idx < R * R; idx += nthr) {
-        const int j = idx / R, k = idx % R;
-        if (j <= k) {
-            const double gj = sh.g[j], gk = sh.g[k];
-            ps.asm2[gram_off(R, j) + (k - j)] = t2[gram_off(R, j) + (k - j)] + (t2[NGm + j] * gk + gj * t2[NGm + k]) + kappa * gj * gk;
-        }
-    }
-    if (tid >= nthr - R) {
-        const int j = tid - (nthr - R);
-        ps.asm2[NGm + j] = fma(psi, sh.g[j], t2[NGm + R + j]);
-    }
-    sync_n<BAR>(nthr);
-    // bu = h - A xbar ; q1 = gamma - 2 xbar'h + xbar'A xbar   (warp 0)
-    if (tid < 32) {
-        const int lane = tid;
-        double ax = 0.0, hj = 0.0, xj = 0.0;
-        if (lane < R) {
-            double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-            for (int k = 0; k < R; k += 2) {
-                const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
-                a0 = fma(ps.asm2[gram_off(R, lo) + hi - lo], sh.xb[k], a0);
-                if (k + 1 < R) {
-                    const int lo1 = k + 1 < lane ? k + 1 : lane, hi1 = k + 1 < lane ? lane : k + 1;
-                    a1 = fma(ps.asm2[gram_off(R, lo1) + hi1 - lo1], sh.xb[k + 1], a1);
-                }
-            }
-            ax = a0 + a1;
-            hj = ps.asm2[NGm + lane];
-            xj = sh.xb[lane];
-        }
-        const double xh = warp_allsum(xj * hj);
-        const double xax = warp_allsum(xj * ax);
-        const double w1 = sh.w1, w0 = sh.w0;
-        const double q1 = gamma - 2.0 * xh + xax;
-        const double q0 = t2[NGm + 2 * R + 3];
-        if (lane < R) sh.tot[NGm + lane] = w1 * (hj - ax);                     // b = w1 sum m e c
-        if (lane == 0) {
-            sh.tot[NGm + R + 0] = w1 * q1 + w0 * q0;                           // s = diff' Ri diff
-            sh.tot[NGm + R + 1] = q1;
-            sh.tot[NGm + R + 2] = q0;
-            sh.tot[NGm + R + 3] = t2[NGm + 2 * R + 4];
-        }
-    }
-    {
-        const double w1 = sh.w1;
-        for (int idx = tid; idx < NGm; idx += nthr) sh.tot[idx] = w1 * ps.asm2[idx];   // G = w1 A_t
-    }
-    sync_n<BAR>(nthr);
+// ---- parameter sets {g_{s-1}, xbar_s}: control CTA -> data CTAs through global memory --------------------
+// One 16-byte cell per double, {lo, tag, hi, tag} with tag = s + 1: every 8-byte half carries its own tag, so
+// a reader that polls the cell needs no separate flag (one L2 round trip instead of two) and never sees a torn
+// value.  p.gparams = [2 parities][2R] cells, zeroed by the host before every launch.
+__device__ __forceinline__ void cell_store(uint4* cell, double v, uint32_t tag) {
+    const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __forceinline__ double cell_poll(const uint4* cell, uint32_t tag) {
+    uint32_t lo, t0, hi, t1;
+    do {
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(cell) : "memory");
+    } while (t0 != tag || t1 != tag);
+    return __hiloint2double((int)hi, (int)lo);
 }
 
-template <int R, typename T, int NSOLVE>
-__global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KParams p) {
-    using L = SlotLayout<R, T>;
+// named barriers of the control CTA
+constexpr int CB_GJ = 1;           // elimination threads
+constexpr int CB_S = 2;            // solver group
+constexpr int CB_R = 3;            // reducer group
+constexpr int CB_FULL = 4;         // +parity: reducers arrive, solvers wait     (statistics of a step are complete)
+constexpr int CB_EMPTY = 6;        // +parity: solvers arrive, reducers wait     (statistics buffer may be overwritten)
+constexpr int C_SOLVERS = 256;     // threads [0, 256): r x r update;  [256, 512): reduction + NVLink exchange
+constexpr int C_GJ = 192;          // elimination threads; the two remaining solver warps do the side computations
+
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int R>
+struct ControlSmem {
+    Smem<R> sh;
+    double tot2[2][nstat2_pad(R)];   // reduced (and exchanged) pipelined sums of step t in tot2[t & 1]
+    double tmp2[nstat2_pad(R)];      // exchange scratch (reducers)
+    double a2[nstat2_pad(R)];        // A_t packed, h_t, gamma, q0, n_obs (solvers)
+    double kb[R];                    // K b
+};
+
+// ---- reducer half of the control CTA -------------------------------------------------------------------
+template <int R>
+__device__ void control_reduce(const KParams& p, ControlSmem<R>& cs) {
     constexpr int NSP2 = nstat2_pad(R), NST2 = nstat2(R);
-    constexpr int NPW = s_npass(NSOLVE);
-    constexpr int NSV = NSOLVE * 32;                            // solver threads
-    constexpr int BAR_RED = 0, BAR_GJ = 1, BAR_XB0 = 2, BAR_SOLVE = 3;
-    extern __shared__ __align__(128) unsigned char dyn_smem_s[];
-    __shared__ Smem<R> sh;
-    __shared__ __align__(8) PipeSmem<R> ps;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int series = blockIdx.x / p.cps;
-    const int part = blockIdx.x % p.cps;
-    const int ntiles = (int)((p.d + TILE - 1) / TILE);
-    const int tb = (int)((int64_t)ntiles * part / p.cps);
-    const int te = (int)((int64_t)ntiles * (part + 1) / p.cps);
-    const int nt = te - tb;
-    const bool writer = part == 0;
-    const int nslot = p.nslot;
-    const int64_t n = p.n_steps;
-
-    unsigned char* slots = dyn_smem_s;
-    double* ebuf = reinterpret_cast<double*>(dyn_smem_s + (size_t)nslot * L::SLOT);
-    T* Cs = reinterpret_cast<T*>(p.C) + (int64_t)series * p.c_series_stride;
-    double* stg = p.state + (int64_t)series * st_size(R);
-
-    if (tid == 0) {
-        for (int s = 0; s < nslot; ++s) {
-            mbar_init(&ps.full[s], 1);
-            mbar_init(&ps.done[s], L::TS);
+    const int tid = threadIdx.x - C_SOLVERS, lane = tid & 31, warp = tid >> 5;
+    constexpr int NTHR = 512 - C_SOLVERS, NW = NTHR / 32;
+    const int ndata = p.cps;
+    const int pstr = (ndata + 7) & ~7;
+    for (int64_t t = 0; t < p.n_steps; ++t) {
+        const int b = (int)(t & 1);
+        double* tot2 = cs.tot2[b];
+        if (t >= 2) named_bar_sync(CB_EMPTY + b, 512);             // the solvers are done with the sums of step t-2
+        stamp(p, t, 2, C_SOLVERS);
+        if (tid == 0) {
+            const unsigned long long target = (unsigned long long)ndata * (unsigned long long)(t / 2 + 1);
+            while (ld_acquire_gpu(p.bar + b) < target) {
+            }
         }
-        mbar_init(&ps.stats_full[0], NPW);
-        mbar_init(&ps.stats_full[1], NPW);
-        mbar_init(&ps.red_free, 1);
-        mbar_init(&ps.par_full[0], 1);
-        mbar_init(&ps.par_full[1], 1);
-        mbar_init(&ps.tot_full[0], 1);
-        mbar_init(&ps.tot_full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        stamp(p, t, 3, C_SOLVERS);
+        sync_n<CB_R>(NTHR);
+        // deterministic sum of the CTA partials [entry][cta]: one warp per entry, 4 entries in flight, lanes over
+        // pairs of CTAs (16-byte coalesced loads), fixed in-lane order and a fixed xor tree across the lanes
+        {
+            const double* base = p.partials + (size_t)b * NSP2 * pstr;
+            constexpr int EB = 4;
+            for (int e0 = warp; e0 < NST2; e0 += NW * EB) {
+                double2 v[EB][4];
+                // unconditional loads from clamped addresses (all EB * 4 in flight), masked afterwards
+#pragma unroll
+                for (int q = 0; q < EB; ++q) {
+                    const int e = min(e0 + NW * q, NST2 - 1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = min(2 * (lane + 32 * j), pstr - 2);
+                        v[q][j] = __ldcg(reinterpret_cast<const double2*>(base + (size_t)e * pstr + c));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < EB; ++q) {
+                    const int e = e0 + NW * q;
+                    double h[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 2 * (lane + 32 * j);
+                        h[j] = (c < ndata ? v[q][j].x : 0.0) + (c + 1 < ndata ? v[q][j].y : 0.0);
+                    }
+                    const double sum = warp_allsum((h[0] + h[1]) + (h[2] + h[3]));
+                    if (lane == 0 && e < NST2) tot2[e] = sum;
+                }
+            }
+            sync_n<CB_R>(NTHR);
+        }
+        stamp(p, t, 4, C_SOLVERS);
+        if (p.world > 1) gpu_exchange<NST2, NSP2, CB_R>(p, tot2, cs.tmp2, tid, t, 0, NTHR);
+        stamp(p, t, 13, C_SOLVERS);
+        __threadfence_block();
+        named_bar_arrive(CB_FULL + b, 512);
     }
-    for (int i = tid; i < R * R; i += blockDim.x) {
+}
+
+// ---- solver half of the control CTA --------------------------------------------------------------------
+// Per step: assemble the statistics of step t from the pipelined sums (+ g_{t-1}, xbar_t), solve for K, update
+// x and publish {g_t, xbar_{t+1}} as early as possible (that is all the data CTAs wait for); the rest of the
+// r x r update (omega, phi, P, V, Q, rho, lambda, the next predict) follows off the critical path.
+// rPSMF.py:102-115,133-135 with the statistics in the sufficient-statistic form of psmf_filter.cuh.
+template <int R>
+__device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
+    constexpr int NGm = ngram(R);
+    constexpr int NTHR = C_SOLVERS;
+    constexpr int FIN = R & 1;
+    Smem<R>& sh = cs.sh;
+    double* a2 = cs.a2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = p.n_steps;
+    const bool simp = (p.flags & F_SIMPLIFIED) != 0;
+    const bool robust = (p.flags & F_ROBUST) != 0;
+    const double dg = (double)p.d_global;
+    double* stg = p.state;
+    uint4* cells = reinterpret_cast<uint4*>(p.gparams);
+
+    for (int i = tid; i < R * R; i += NTHR) {
         sh.P[i] = stg[st_P(R) + i];
         sh.V[i] = stg[st_V(R) + i];
         sh.Q[i] = stg[st_Q(R) + i];
@@ -492,99 +540,326 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
         sh.rho = stg[st_rho(R)];
         sh.lam = stg[st_lam(R)];
     }
+    sync_n<CB_S>(NTHR);
+    predict_cta<R, CB_S>(p, sh, tid, p.k0, 0, NTHR);               // xbar_0, Pbar_0, a_0, w1/w0
+    if (tid < R) {                                                 // set 0 = {0, xbar_0}
+        cell_store(cells + tid, 0.0, 1u);
+        cell_store(cells + R + tid, sh.xb[tid], 1u);
+    }
+
+    for (int64_t t = 0; t < n; ++t) {
+        const int b = (int)(t & 1);
+        const double* t2 = cs.tot2[b];
+        stamp(p, t, 0);
+        named_bar_sync(CB_FULL + b, 512);
+        stamp(p, t, 1);
+        // (A) A_t = A0 + u g' + g u' + kappa g g' (packed upper triangle), h_t = h0 + psi g, scalars
+        {
+            const double kappa = t2[NGm + 2 * R + 0], psi = t2[NGm + 2 * R + 1];
+            for (int idx = tid; idx < R * R; idx += NTHR) {
+                const int j = idx / R, k = idx % R;
+                if (j <= k) {
+                    const double gj = sh.g[j], gk = sh.g[k];
+                    a2[gram_off(R, j) + (k - j)] = t2[gram_off(R, j) + (k - j)] + (t2[NGm + j] * gk + gj * t2[NGm + k]) + kappa * gj * gk;
+                }
+            }
+            if (tid >= NTHR - R) {
+                const int j = tid - (NTHR - R);
+                a2[NGm + j] = fma(psi, sh.g[j], t2[NGm + R + j]);
+            }
+            if (tid < 3) a2[NGm + R + tid] = t2[NGm + 2 * R + 2 + tid];     // gamma, q0, n_obs
+        }
+        sync_n<CB_S>(NTHR);
+        named_bar_arrive(CB_EMPTY + b, 512);                        // cs.tot2[b] may be refilled (step t+2)
+        // (B) augmented matrix [I + Pbar G | Pbar], G = w1 A_t
+        if (!simp) {
+            const double w1 = sh.w1;
+            for (int idx = tid; idx < R * R; idx += NTHR) {
+                const int i = idx / R, j = idx % R;
+                double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < R; k += 2) {
+                    const int lo = k < j ? k : j, hi = k < j ? j : k;
+                    acc0 = fma(sh.Pb[i * R + k], a2[gram_off(R, lo) + hi - lo], acc0);
+                    if (k + 1 < R) {
+                        const int lo1 = k + 1 < j ? k + 1 : j, hi1 = k + 1 < j ? j : k + 1;
+                        acc1 = fma(sh.Pb[i * R + k + 1], a2[gram_off(R, lo1) + hi1 - lo1], acc1);
+                    }
+                }
+                sh.aug[0][i][j] = fma(w1, acc0 + acc1, (i == j) ? 1.0 : 0.0);
+                sh.aug[0][i][R + j] = sh.Pb[i * R + j];
+            }
+            sync_n<CB_S>(NTHR);
+        }
+        // (C) elimination (C_GJ threads) next to the side computations (two warps)
+        if (tid < C_GJ) {
+            if (!simp) gauss_jordan_cta<R, C_GJ, CB_GJ, 2 * R>(sh, tid);      // aug[FIN][perm[k]][R..2R) = K[k][:]
+        } else if (warp == C_GJ / 32) {
+            // b = w1 (h - A xbar), q1 = gamma - 2 xbar'h + xbar'A xbar, s = w1 q1 + w0 q0
+            double ax = 0.0, hj = 0.0, xj = 0.0;
+            if (lane < R) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < R; k += 2) {
+                    const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
+                    s0 = fma(a2[gram_off(R, lo) + hi - lo], sh.xb[k], s0);
+                    if (k + 1 < R) {
+                        const int lo1 = k + 1 < lane ? k + 1 : lane, hi1 = k + 1 < lane ? lane : k + 1;
+                        s1 = fma(a2[gram_off(R, lo1) + hi1 - lo1], sh.xb[k + 1], s1);
+                    }
+                }
+                ax = s0 + s1;
+                hj = a2[NGm + lane];
+                xj = sh.xb[lane];
+            }
+            const double xh = warp_allsum(xj * hj);
+            const double xax = warp_allsum(xj * ax);
+            const double w1 = sh.w1, w0 = sh.w0;
+            const double q1 = a2[NGm + R + 0] - 2.0 * xh + xax;
+            const double q0 = a2[NGm + R + 1];
+            if (lane < R) sh.tot[NGm + lane] = w1 * (hj - ax);                 // b = w1 sum m e c
+            if (lane == 0) {
+                sh.tot[NGm + R + 0] = w1 * q1 + w0 * q0;                       // s = diff' Ri diff
+                sh.tot[NGm + R + 1] = q1;
+                sh.tot[NGm + R + 2] = q0;
+                sh.tot[NGm + R + 3] = a2[NGm + R + 2];
+            }
+        } else {
+            // eta = (rho n_obs + (rho + a) tr(Pbar G)) / d, N = a + eta, g_t = V x_bar / N   (rPSMF.py:108-111)
+            const double a = sh.a, rho = sh.rho;
+            double eta;
+            if (simp) {
+                eta = rho;                                                     // synthetic_psmf.py:86-87
+            } else {
+                double tr = 0.0;
+                if (lane < R) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < R; i += 2) {
+                        const int lo = i < lane ? i : lane, hi = i < lane ? lane : i;
+                        s0 = fma(sh.Pb[i * R + lane], a2[gram_off(R, lo) + hi - lo], s0);
+                        if (i + 1 < R) {
+                            const int lo1 = i + 1 < lane ? i + 1 : lane, hi1 = i + 1 < lane ? lane : i + 1;
+                            s1 = fma(sh.Pb[(i + 1) * R + lane], a2[gram_off(R, lo1) + hi1 - lo1], s1);
+                        }
+                    }
+                    tr = s0 + s1;
+                }
+                const double trpg = sh.w1 * warp_allsum(tr);
+                eta = (rho * a2[NGm + R + 2] + (rho + a) * trpg) / dg;
+            }
+            const double N = a + eta;
+            if (lane < R) sh.g[lane] = (((p.flags & F_CUPDATE_VT) != 0) ? sh.vx[lane] : sh.vxt[lane]) / N;   // rPSMF.py:111 / PSMF.py:80
+            if (lane == 0) {
+                sh.sc[1] = eta;
+                sh.sc[2] = N;
+            }
+        }
+        sync_n<CB_S>(NTHR);
+        stamp(p, t, 7);
+        // (D) x_t = xbar_t + K b, xbar_{t+1} = f(x_t); publish set t+1 = {g_t, xbar_{t+1}}   (warp 0)
+        if (warp == 0) {
+            const int j = lane & 15, half = lane >> 4;
+            double kbj = 0.0;
+            if (!simp && j < R) {
+                const double* Krow = &sh.aug[FIN][sh.perm[j]][R];
+                double s0 = 0.0, s1 = 0.0;
+                constexpr int H = (R + 1) / 2;
+#pragma unroll
+                for (int k = 0; k < H; k += 2) {
+                    const int k0 = half * H + k;
+                    if (k0 < R) s0 = fma(Krow[k0], sh.tot[NGm + k0], s0);
+                    if (k + 1 < H && k0 + 1 < R) s1 = fma(Krow[k0 + 1], sh.tot[NGm + k0 + 1], s1);
+                }
+                kbj = s0 + s1;
+            }
+            kbj += __shfl_xor_sync(FULL, kbj, 16);
+            double xn = 0.0, xnext = 0.0;
+            if (lane < R) {
+                xn = sh.xb[lane] + kbj;                                        // rPSMF.py:104 (simplified: x = x_bar)
+                if (p.dynamics == DYN_COS) {
+                    const double arg = __dadd_rn(__dmul_rn(__dmul_rn(6.283185307179586, sh.th[lane]), (double)(p.k0 + t + 1)), xn);
+                    xnext = cos(arg);
+                } else {
+                    xnext = xn;                        // external dynamics run one step per launch: set n is never used
+                }
+                cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + lane, sh.g[lane], (uint32_t)(t + 2));
+                cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + R + lane, xnext, (uint32_t)(t + 2));
+                cs.kb[lane] = kbj;
+            }
+            stamp(p, t, 6);
+            // (E) off the critical path: omega, phi, gradient of the step log-likelihood
+            const double a = sh.a, rho = sh.rho, lam = sh.lam;
+            const double s = sh.tot[NGm + R], q1 = sh.tot[NGm + R + 1], q0 = sh.tot[NGm + R + 2], nobs = sh.tot[NGm + R + 3];
+            const double eta = sh.sc[1], N = sh.sc[2];
+            const double bkb = warp_allsum((lane < R && !simp) ? sh.tot[NGm + lane] * kbj : 0.0);
+            const double sSe = s - bkb;                                        // diff' CPinv diff (simplified: s)
+            const double omega = robust ? (lam + sSe) / (lam + dg) : 1.0;      // rPSMF.py:105
+            const double phi = robust ? (lam + q1 / N + (q0 != 0.0 ? q0 / eta : 0.0)) / (lam + dg) : 1.0;
+            if (lane < R) {
+                sh.x[lane] = xn;
+                if (p.X_out != nullptr) p.X_out[t * R + lane] = xn;
+                if (p.grad_out != nullptr && p.dynamics == DYN_COS) {
+                    // d ell_k / d theta = J_theta' d ell_k / d f (psmf.py:57-64,167-177; rpsmf.py:62-71,196-200)
+                    const double vsf = 0.5 * (sh.vx[lane] + sh.vxt[lane]);
+                    const double cte = sh.tot[NGm + lane] * (rho + a);
+                    double gf;
+                    if ((p.flags & F_LL_STUDENT) != 0) {
+                        const double gq = 1.0 + q1 / (lam * N);
+                        gf = nobs * vsf / N - (nobs + lam) / (gq * lam * N) * (cte + (q1 / N) * vsf);
+                    } else {
+                        gf = (nobs / N - q1 / (N * N)) * vsf - cte / N;
+                    }
+                    sh.grad[lane] += gf * (6.283185307179586 * (double)(p.k0 + t) * sh.fd[lane]);
+                }
+            }
+            if (lane == 0) {
+                sh.sc[0] = omega; sh.sc[3] = phi; sh.sc[4] = sSe;
+                sh.sc[5] = p.alpha * phi; sh.sc[6] = p.beta * omega;
+                if (p.scal_out != nullptr) {
+                    double* so = p.scal_out + t * NSCAL;
+                    so[0] = a; so[1] = eta; so[2] = N; so[3] = omega; so[4] = phi; so[5] = sSe; so[6] = lam; so[7] = rho;
+                }
+                if (!(isfinite(N) && isfinite(omega) && isfinite(phi) && isfinite(xn)) || N == 0.0)
+                    atomicCAS((unsigned long long*)p.status, ~0ULL, (unsigned long long)t);
+            }
+            __syncwarp();
+        }
+        sync_n<CB_S>(NTHR);
+        {
+            const double omega = sh.sc[0], N = sh.sc[2], aphi = sh.sc[5], bom = sh.sc[6];
+            for (int idx = tid; idx < R * R; idx += NTHR) {
+                const int i = idx / R, j = idx % R;
+                const double pn = simp ? sh.Pb[idx] : bom * sh.aug[FIN][sh.perm[i]][R + j];      // rPSMF.py:106
+                const double vn = aphi * (sh.V[idx] - sh.vx[i] * sh.vxt[j] / N);                 // rPSMF.py:115
+                sh.P[idx] = pn;
+                sh.V[idx] = vn;
+                if (!simp) sh.Q[idx] = omega * sh.Q[idx];                                        // rPSMF.py:133
+            }
+            if (tid == NTHR - 32) {
+                const double lam = sh.lam;
+                sh.rho = omega * sh.rho;                                                         // rPSMF.py:134
+                sh.lam = (robust && (p.flags & F_FIXED_LAMBDA) == 0) ? lam + dg : lam;           // rPSMF.py:135
+            }
+        }
+        sync_n<CB_S>(NTHR);
+        if (t + 1 < n) predict_cta<R, CB_S>(p, sh, tid, p.k0 + t + 1, 0, NTHR);
+        stamp(p, t, 12);
+    }
+    for (int i = tid; i < R * R; i += NTHR) {
+        stg[st_P(R) + i] = sh.P[i];
+        stg[st_V(R) + i] = sh.V[i];
+        stg[st_Q(R) + i] = sh.Q[i];
+    }
+    if (tid < R) {
+        stg[st_x(R) + tid] = sh.x[tid];
+        if (p.grad_out != nullptr) p.grad_out[tid] = sh.grad[tid];
+    }
+    if (tid == 0) {
+        stg[st_rho(R)] = sh.rho;
+        stg[st_lam(R)] = sh.lam;
+    }
+}
+
+// pass warp 0 polls parameter set `set` in global memory into ps.par[set & 1] and releases the other warps
+template <int R>
+__device__ __forceinline__ void fetch_params(const KParams& p, DataSmem<R>& ps, int64_t set, int wp, int lane) {
+    if (wp == 0) {
+        const uint4* cells = reinterpret_cast<const uint4*>(p.gparams) + (size_t)(set & 1) * 2 * R;
+        for (int i = lane; i < 2 * R; i += 32) ps.par[set & 1][i] = cell_poll(cells + i, (uint32_t)(set + 1));
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ps.par_full[set & 1]);
+    }
+    mbar_wait(&ps.par_full[set & 1], (uint32_t)((set >> 1) & 1));
+}
+
+template <int R, typename T>
+__global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KParams p) {
+    if (p.trace != nullptr && threadIdx.x == 0 && (int)blockIdx.x < p.trace_steps) {   // debug: SM id of every CTA (row 159)
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[(size_t)p.trace_steps * 16 + (size_t)159 * p.trace_steps + blockIdx.x] = smid;
+    }
+    // a CTA is either the control CTA or a data CTA: their static shared state shares one buffer
+    constexpr size_t SBYTES = sizeof(ControlSmem<R>) > sizeof(DataSmem<R>) ? sizeof(ControlSmem<R>) : sizeof(DataSmem<R>);
+    __shared__ __align__(16) unsigned char static_smem[SBYTES];
+    if (blockIdx.x == gridDim.x - 1) {       // ---- control CTA ----
+        ControlSmem<R>& cs = *reinterpret_cast<ControlSmem<R>*>(static_smem);
+        if (threadIdx.x < C_SOLVERS) control_solve<R>(p, cs);
+        else control_reduce<R>(p, cs);
+        return;
+    }
+    using L = SlotLayout<R, T>;
+    const int NPW = p.npw;                                         // active pass warps (<= V2_PASS_WARPS)
+    extern __shared__ __align__(128) unsigned char dyn_smem_s[];
+    DataSmem<R>& ps = *reinterpret_cast<DataSmem<R>*>(static_smem);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int part = blockIdx.x;                                   // data CTA index, p.cps data CTAs
+    const int ntiles = (int)((p.d + TILE - 1) / TILE);
+    const int tb = (int)((int64_t)ntiles * part / p.cps);
+    const int te = (int)((int64_t)ntiles * (part + 1) / p.cps);
+    const int nt = te - tb;
+    const int nslot = p.nslot;
+    const int64_t n = p.n_steps;
+
+    unsigned char* slots = dyn_smem_s;
+    double* ebuf = reinterpret_cast<double*>(dyn_smem_s + (size_t)nslot * L::SLOT);
+    T* Cs = reinterpret_cast<T*>(p.C);
+
+    if (tid == 0) {
+        for (int s = 0; s < nslot; ++s) {
+            mbar_init(&ps.full[s], 1);
+            mbar_init(&ps.done[s], L::TS);
+        }
+        mbar_init(&ps.par_full[0], 1);
+        mbar_init(&ps.par_full[1], 1);
+        ps.arrived = 0;
+        ps.sum_done = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = tid; i < nt * TILE; i += blockDim.x) ebuf[i] = 0.0;
     __syncthreads();
 
-    if (warp == V2_CWARPS) {                 // ---- producer warp ----
+    if (warp == V2_PASS_WARPS) {             // ---- producer warp ----
         if (lane == 0) s_producer<R, T>(p, ps, slots, Cs, tb, nt, nslot);
         return;
     }
 
-    if (warp == 0) {
-        // ---- reducer warp: partial sums of pass t -> grid (and GPU) totals of step t ----
-        for (int64_t t = 0; t < n; ++t) {
-            stamp(p, t, 0);
-            mbar_wait(&ps.stats_full[t & 1], (uint32_t)((t >> 1) & 1));
-            stamp(p, t, 1);
-            for (int e = lane; e < NST2; e += 32) {                     // CTA partial: fixed order over the pass warps
-                double s = 0.0;
-#pragma unroll
-                for (int w = 0; w < NPW; ++w) s += sh.red[w * NSP2 + e];
-                ps.part2[e] = s;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ps.red_free);
-            stamp(p, t, 2);
-            // tot2[t & 1] was last read by the solve of step t-2, which completed before pass t could start
-            grid_reduce<NST2, NSP2, BAR_RED>(p, ps.part2, ps.tot2[t & 1], lane, lane, 0, t, series, part, 32);
-            __threadfence_block();
-            if (lane == 0) mbar_arrive(&ps.tot_full[t & 1]);
-            stamp(p, t, 5);
-        }
-        return;
-    }
-
-    if (warp <= NSOLVE) {
-        // ---- solver warps: r x r solve of step t (needs the totals of step t and the solve of step t-1) ----
-        const int st = tid - 32, swarp = warp - 1;
-        predict_cta<R, BAR_SOLVE>(p, sh, st, p.k0, series, NSV);       // xbar_0, Pbar_0, a_0, w1/w0
-        if (st < R) ps.xb0[st] = sh.xb[st];
-        __threadfence_block();
-        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_XB0), "r"(NSV + NPW * 32) : "memory");     // xbar_0 is published
-        for (int64_t t = 0; t < n; ++t) {
-            mbar_wait(&ps.tot_full[t & 1], (uint32_t)((t >> 1) & 1));
-            if (st == 0) stamp_pass(p, t, 12, 0, true);
-            assemble_stats<R, BAR_SOLVE>(sh, ps, ps.tot2[t & 1], st, NSV);
-            small_update<R, NSV, BAR_SOLVE, BAR_GJ>(p, sh, st, lane, swarp, series, t, writer, NSV);
-            // publish g_t and xbar_{t+1} for pass t+2 (small_update ended with a barrier over the solver threads)
-            if (st < R) {
-                ps.par[t & 1][st] = sh.g[st];
-                ps.par[t & 1][R + st] = sh.xb[st];
-            }
-            sync_n<BAR_SOLVE>(NSV);
-            if (st == 0) {
-                mbar_arrive(&ps.par_full[t & 1]);
-                stamp_pass(p, t, 13, 0, true);
-            }
-        }
-        if (writer) {
-            for (int i = st; i < R * R; i += NSV) {
-                stg[st_P(R) + i] = sh.P[i];
-                stg[st_V(R) + i] = sh.V[i];
-                stg[st_Q(R) + i] = sh.Q[i];
-            }
-            if (st < R) {
-                stg[st_x(R) + st] = sh.x[st];
-                if (p.grad_out != nullptr) p.grad_out[(int64_t)series * R + st] = sh.grad[st];
-            }
-            if (st == 0) {
-                stg[st_rho(R)] = sh.rho;
-                stg[st_lam(R)] = sh.lam;
-            }
-        }
-        return;
-    }
-
     // ---- pass warps ----
-    const int wp = warp - 1 - NSOLVE;
-    const T* Yb = reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst;
-    const uint8_t* Mb = p.M != nullptr ? p.M + (int64_t)series * p.msst : nullptr;
-    asm volatile("bar.sync %0, %1;" ::"n"(BAR_XB0), "r"(NSV + NPW * 32) : "memory");   // xbar_0 available
+    const int wp = warp;
+    if (wp >= NPW) return;
+    const T* Yb = reinterpret_cast<const T*>(p.Y);
+    const uint8_t* Mb = p.M;
     for (int64_t pass = 0; pass < n; ++pass) {
-        // pass `pass` needs the solve of step pass-2 (g_{pass-2}, xbar_{pass-1})
         if (wp == 0 && lane == 0) stamp_pass(p, pass, 11, 0, true);
-        if (pass >= 2) mbar_wait(&ps.par_full[(pass - 2) & 1], (uint32_t)(((pass - 2) >> 1) & 1));
-        if (wp == 0 && lane == 0) stamp_pass(p, pass, 8, 0, true);
-        T* Yrec_prev = (p.Yrec && pass >= 1) ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + (pass - 1) * p.ldrec : nullptr;
-        s_warp_pass<R, T, false, NPW>(p, ps, ebuf, slots, sh.red, Yrec_prev, Yb, Mb, tb, nt, nslot, pass, wp, lane);
-        if (wp == 0 && lane == 0) stamp_pass(p, pass, 9, 0, true);
+        if (pass >= 1) fetch_params<R>(p, ps, pass - 1, wp, lane);   // {g_{pass-2}, xbar_{pass-1}}
+        if (wp == 0 && lane == 0) {
+            stamp_pass(p, pass, 8, 0, true);
+            if (p.trace != nullptr && pass < p.trace_steps) {      // per-CTA pass start times (second block)
+                unsigned long long v;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+                p.trace[(size_t)p.trace_steps * (16 + 160) + (size_t)blockIdx.x * p.trace_steps + pass] = v;
+            }
+        }
+        T* Yrec_prev = (p.Yrec && pass >= 1) ? reinterpret_cast<T*>(p.Yrec) + (pass - 1) * p.ldrec : nullptr;
+        s_warp_pass<R, T, false>(p, ps, ebuf, slots, Yrec_prev, Yb, Mb, tb, nt, nslot, pass, wp, lane, NPW);
+        if (wp == 0 && lane == 0) {
+            stamp_pass(p, pass, 9, 0, true);
+            if (p.trace != nullptr && pass < p.trace_steps) {      // per-CTA pass end times behind the 16-entry rows
+                unsigned long long v;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+                p.trace[(size_t)p.trace_steps * 16 + (size_t)blockIdx.x * p.trace_steps + pass] = v;
+            }
+        }
     }
-    // flush: both pending rank-1 updates -> C_n; needs the solves of steps n-2 and n-1
-    if (n >= 2) mbar_wait(&ps.par_full[(n - 2) & 1], (uint32_t)(((n - 2) >> 1) & 1));
-    mbar_wait(&ps.par_full[(n - 1) & 1], (uint32_t)(((n - 1) >> 1) & 1));
+    // flush: both pending rank-1 updates -> C_n; needs the parameter sets n-1 (fetched for pass n-1.. or now) and n
+    fetch_params<R>(p, ps, n - 1, wp, lane);
+    fetch_params<R>(p, ps, n, wp, lane);
     {
-        T* Yrec_prev = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + (n - 1) * p.ldrec : nullptr;
-        s_warp_pass<R, T, true, NPW>(p, ps, ebuf, slots, sh.red, Yrec_prev, Yb, Mb, tb, nt, nslot, n, wp, lane);
+        T* Yrec_prev = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (n - 1) * p.ldrec : nullptr;
+        s_warp_pass<R, T, true>(p, ps, ebuf, slots, Yrec_prev, Yb, Mb, tb, nt, nslot, n, wp, lane, NPW);
     }
 }
 

@@ -10,10 +10,9 @@
 
 namespace psmf {
 
-// p.nsolve selects the warp configuration: 2 solver warps + 12 pass warps (streaming) or 5 + 9 (resident)
-template <typename T, int NSOLVE>
-static cudaError_t launch_c(const KParams& p, int grid, size_t dyn, cudaStream_t st, bool coop) {
-    auto kern = psmf_stream_kernel<PSMF_R, T, NSOLVE>;
+template <typename T>
+static cudaError_t launch_t(const KParams& p, int grid, size_t dyn, cudaStream_t st, bool coop) {
+    auto kern = psmf_stream_kernel<PSMF_R, T>;
     constexpr int threads = s_threads();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
@@ -25,21 +24,10 @@ static cudaError_t launch_c(const KParams& p, int grid, size_t dyn, cudaStream_t
     kern<<<grid, threads, dyn, st>>>(p);
     return cudaGetLastError();
 }
-template <typename T>
-static cudaError_t launch_t(const KParams& p, int grid, size_t dyn, cudaStream_t st, bool coop) {
-    return p.nsolve >= 5 ? launch_c<T, 5>(p, grid, dyn, st, coop) : launch_c<T, 2>(p, grid, dyn, st, coop);
-}
 
 template <typename T>
 static cudaError_t shape_t(size_t dyn, LaunchShape* out) {
-    auto kern = psmf_stream_kernel<PSMF_R, T, 2>;
-    {
-        auto kern5 = psmf_stream_kernel<PSMF_R, T, 5>;
-        if (dyn > 0) {
-            cudaError_t e5 = cudaFuncSetAttribute(kern5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            if (e5 != cudaSuccess) return e5;
-        }
-    }
+    auto kern = psmf_stream_kernel<PSMF_R, T>;
     constexpr int threads = s_threads();
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, kern);

@@ -254,7 +254,7 @@ class FilterEngine:
 
     def set_trace(self, steps):
         """Debug: record phase time stamps (ns, globaltimer) of CTA 0 for the first `steps` steps of each run."""
-        self._trace = torch.zeros((steps, 16), dtype=torch.int64, device=self.device) if steps else None
+        self._trace = torch.zeros((steps * (16 + 320),), dtype=torch.int64, device=self.device) if steps else None
         self._ck(self._L.psmf_set_trace(self._h, C.c_void_p(self._trace.data_ptr()) if steps else None, int(steps)))
         return self._trace
 
