@@ -258,7 +258,7 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
         CKC(cudaMalloc(&e->partials, (size_t)2 * nsp * (pstr > 17 ? pstr : 17) * sizeof(double)));   // also >= 2 * cps2 * nstat2_pad
     }
     CKC(cudaMalloc(&e->bar, 8 * sizeof(unsigned long long)));
-    CKC(cudaMalloc(&e->gparams, 4 * MAXR * 16));                        // [2][2R] 16-byte cells (psmf_stream.cuh)
+    CKC(cudaMalloc(&e->gparams, GPARAMS_BYTES));                        // 16-byte cells (psmf_stream.cuh): parameter sets [2][2R], totals [2][nstat2_pad]
     CKC(cudaMalloc(&e->status, sizeof(long long)));
     CKC(cudaMemset(e->status, 0xFF, sizeof(long long)));
     if (cfg->world_size > 1) {
@@ -377,7 +377,7 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     }
     p.trace = h->trace; p.trace_steps = h->trace_steps;
     CK(h, cudaMemsetAsync(h->bar, 0, 8 * sizeof(unsigned long long), st));
-    CK(h, cudaMemsetAsync(h->gparams, 0, 4 * MAXR * 16, st));
+    CK(h, cudaMemsetAsync(h->gparams, 0, GPARAMS_BYTES, st));
     CK(h, cudaMemsetAsync(h->status, 0xFF, sizeof(long long), st));
     // the TMA-staged kernel needs 16-byte aligned rows of Y / M (bulk copies)
     const size_t es = h->esize;

@@ -33,7 +33,7 @@ constexpr int F_DBG_NOCOMPUTE = 1 << 20, F_DBG_NOSTORE = 1 << 21, F_DBG_NOYM = 1
 __host__ __device__ constexpr int tile_pos(int j, int i) { return j * 32 + (i ^ ((j & 7) << 2)); }
 
 constexpr int V1_WARPS = 8;     // direct-load kernel: warps per CTA (one tile per warp at a time)
-constexpr int V2_CWARPS = 15;   // TMA-staged kernel: consumer warps (+1 producer warp)
+constexpr int V2_CWARPS = 14;   // TMA-staged kernel: pass warps (+1 reduce warp, +1 producer warp)
 constexpr int V2_TS = 4;        // TMA-staged kernel: tiles per shared-memory chunk slot
 constexpr int MAXW = 12;        // max warps that write per-warp partial statistics in any kernel
 
@@ -46,6 +46,8 @@ __host__ __device__ constexpr int nstat2(int R) { return ngram(R) + 2 * R + 5; }
 __host__ __device__ constexpr int nstat2_pad(int R) { return (nstat2(R) + 7) / 8 * 8; }
 // packed index of Gram entry (j, j) in row-major upper-triangular order
 __host__ __device__ constexpr int gram_off(int R, int j) { return j * R - j * (j - 1) / 2; }
+// tagged 16-byte cells behind KParams.gparams: [2][2 MAXR] parameter sets, then [2][nstat2_pad(MAXR)] reduced totals
+constexpr size_t GPARAMS_BYTES = (size_t)(4 * MAXR + 2 * nstat2_pad(MAXR)) * 16;
 
 // small-state layout (doubles per series)
 __host__ __device__ constexpr int st_x(int R) { return 0; }

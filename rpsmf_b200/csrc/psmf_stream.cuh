@@ -44,9 +44,9 @@
 namespace psmf {
 
 constexpr int MAXSLOT = 64;
-constexpr int V2_PASS_WARPS = V2_CWARPS;                           // 15 pass warps + 1 producer warp per data CTA
+constexpr int V2_PASS_WARPS = V2_CWARPS;                           // 14 pass warps + reduce warp + producer warp per data CTA
 
-__host__ __device__ constexpr int s_threads() { return (V2_CWARPS + 1) * 32; }
+__host__ __device__ constexpr int s_threads() { return (V2_CWARPS + 2) * 32; }
 
 __host__ __device__ constexpr size_t round128(size_t x) { return (x + 127) / 128 * 128; }
 template <int R, typename T>
@@ -118,8 +118,8 @@ struct DataSmem {
     uint64_t full[MAXSLOT];        // slot loaded            (producer -> pass warps)
     uint64_t done[MAXSLOT];        // slot processed         (pass warps -> producer)
     uint64_t par_full[2];          // par[s & 1] copied from global memory   (pass warp 0 -> pass warps)
-    volatile int arrived;          // pass warps that have written their partial (monotonic over the launch)
-    volatile int sum_done;         // passes whose CTA partial has been written to global memory
+    uint64_t red_full;             // all pass warps have written red[]      (pass warps -> reduce warp)
+    uint64_t red_free;             // red[] has been read                    (reduce warp -> pass warps)
 };
 
 // per-warp accumulators of one pipelined pass
@@ -166,7 +166,7 @@ template <int R, typename T, bool FLUSH>
 __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, double* __restrict__ ebuf,
                                             unsigned char* __restrict__ slots, T* __restrict__ Yrec_prev,
                                             const T* __restrict__ Yb, const uint8_t* __restrict__ Mb, int tb, int nt, int nslot,
-                                            int64_t pass, int wp, int lane, int NPW) {
+                                            int64_t pass, int wp, int lane, int NPW, YM<T>& nx) {
     using L = SlotLayout<R, T>;
     constexpr int TS = L::TS, NSP2 = nstat2_pad(R);
     const int nchunks = (nt + TS - 1) / TS;
@@ -180,7 +180,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
     acc.zero();
     long long wait_full = 0;
 
-    YM<T> nx = load_ym<T>(p, Yb, Mb, pass, (int64_t)(tb + wp) * TILE + lane, has_prev, has_cur);
+    // nx = y / m of this warp's first tile, loaded before the wait for the parameter set
     for (int tl = wp; tl < nt; tl += NPW) {
         const YM<T> ym = nx;
         if (tl + NPW < nt)                                             // prefetch y / m of this warp's next tile
@@ -276,10 +276,17 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
         }
     }
     if constexpr (!FLUSH) {
-        if (wp == 0 && lane == 0) stamp_pass(p, pass, 10, (unsigned long long)wait_full, false);
-        // the CTA partial of the previous pass has left the per-warp buffers
-        while (ps.sum_done < (int)pass) {
+        if (wp == 0 && lane == 0) {
+            stamp_pass(p, pass, 10, (unsigned long long)wait_full, false);
+            stamp_pass(p, pass, 14, 0, true);
         }
+        __syncwarp();
+        // y / m of the first tile of the next pass: in flight while this pass is reduced and the next
+        // parameter set is awaited
+        if (pass + 1 <= p.n_steps)
+            nx = load_ym<T>(p, Yb, Mb, pass + 1, (int64_t)(tb + wp) * TILE + lane, true, pass + 1 < p.n_steps);
+        // per-warp sums -> ps.red; the reduce warp adds them and takes it from there, this warp moves on
+        if (pass >= 1) mbar_wait(&ps.red_free, (uint32_t)((pass - 1) & 1));
         double* r0 = ps.red + wp * NSP2;
         const int kq = lane & 3, mm = lane >> 2;
 #pragma unroll
@@ -307,33 +314,10 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
         bfly<5, 16, 5>(acc.v, lane, base, lim);
         if (base < lim) r0[ngram(R) + 2 * R + base] = acc.v[0];
         __syncwarp();
-        // the last warp to arrive adds the per-warp partials in fixed warp order, writes the CTA partial to
-        // global memory and bumps the arrival counter the control CTA is waiting on
-        int last = 0;
-        if (lane == 0) {
-            __threadfence_block();
-            last = (atomicAdd((int*)&ps.arrived, 1) == (int)(pass + 1) * NPW - 1) ? 1 : 0;
-        }
-        last = __shfl_sync(FULL, last, 0);
-        if (last) {
-            __threadfence_block();
-            constexpr int NST2 = nstat2(R);
-            // transposed layout [parity][entry][cta]: the control CTA reads one entry of all CTAs coalesced
-            const int pstr = (p.cps + 7) & ~7;
-            double* gpart = p.partials + (size_t)(pass & 1) * NSP2 * pstr + blockIdx.x;
-            for (int e = lane; e < NST2; e += 32) {
-                double sum = 0.0;
-                for (int w = 0; w < NPW; ++w) sum += ps.red[w * NSP2 + e];
-                gpart[(size_t)e * pstr] = sum;
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                red_release_gpu(p.bar + (pass & 1), 1ULL);
-                ps.sum_done = (int)pass + 1;
-                __threadfence_block();
-            }
-        }
+        if (lane == 0) mbar_arrive(&ps.red_full);
+        __syncwarp();
+        if (wp == 0 && lane == 0) stamp_pass(p, pass, 15, 0, true);
+        __syncwarp();
     }
 }
 
@@ -428,7 +412,7 @@ constexpr int CB_S = 2;            // solver group
 constexpr int CB_R = 3;            // reducer group
 constexpr int CB_FULL = 4;         // +parity: reducers arrive, solvers wait     (statistics of a step are complete)
 constexpr int CB_EMPTY = 6;        // +parity: solvers arrive, reducers wait     (statistics buffer may be overwritten)
-constexpr int C_SOLVERS = 256;     // threads [0, 256): r x r update;  [256, 512): reduction + NVLink exchange
+constexpr int C_SOLVERS = 256;     // threads [0, 256): r x r update;  [256, blockDim): totals + NVLink exchange
 constexpr int C_GJ = 192;          // elimination threads; the two remaining solver warps do the side computations
 
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
@@ -445,63 +429,82 @@ struct ControlSmem {
 };
 
 // ---- reducer half of the control CTA -------------------------------------------------------------------
+// One SM ingests only ~40 GB/s, so the ~200 kB of CTA partials of a step (147 CTAs x 173 doubles at r = 16) are
+// not summed by the control CTA: the reduce warp of data CTA c sums entries c, c + ndata, .. over all CTAs
+// (fixed order: deterministic) and publishes each total as a tagged cell; the control CTA polls the cells.
+template <int R>
+__device__ void reduce_warp(const KParams& p, DataSmem<R>& ps, int lane, int NPW) {
+    constexpr int NSP2 = nstat2_pad(R), NST2 = nstat2(R);
+    constexpr int NE = (NST2 + 31) / 32;
+    const int ndata = p.cps, pstr = (ndata + 7) & ~7, cta = blockIdx.x;
+    uint4* totals = reinterpret_cast<uint4*>(p.gparams) + 4 * MAXR;
+    for (int64_t t = 0; t < p.n_steps; ++t) {
+        const int b = (int)(t & 1);
+        double* base = p.partials + (size_t)b * NSP2 * pstr;
+        // (1) CTA partial of pass t: per-warp sums in fixed warp order -> global [parity][entry][cta]
+        mbar_wait(&ps.red_full, (uint32_t)b);
+        {
+            double sum[NE];
+#pragma unroll
+            for (int i = 0; i < NE; ++i) sum[i] = 0.0;
+            for (int w = 0; w < NPW; ++w) {
+#pragma unroll
+                for (int i = 0; i < NE; ++i) sum[i] += ps.red[w * NSP2 + min(lane + 32 * i, NSP2 - 1)];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ps.red_free);
+#pragma unroll
+            for (int i = 0; i < NE; ++i)
+                if (lane + 32 * i < NST2) base[(size_t)(lane + 32 * i) * pstr + cta] = sum[i];
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                red_release_gpu(p.bar + b, 1ULL);
+                stamp_pass(p, t, 9, 0, true);
+            }
+            __syncwarp();
+        }
+        // (2) this CTA's share of the grid reduction: entries cta, cta + ndata, .. summed over all CTAs
+        if (cta < NST2) {
+            if (lane == 0) {
+                const unsigned long long target = (unsigned long long)ndata * (unsigned long long)(t / 2 + 1);
+                while (ld_acquire_gpu(p.bar + b) < target) {
+                }
+            }
+            __syncwarp();
+            for (int e = cta; e < NST2; e += ndata) {
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldcg(base + (size_t)e * pstr + min(lane + 32 * j, pstr - 1));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = (lane + 32 * j < ndata) ? v[j] : 0.0;
+                const double sum = warp_allsum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])));
+                if (lane == 0) cell_store(totals + (size_t)b * NSP2 + e, sum, (uint32_t)(t + 1));
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ---- reducer half of the control CTA: collect the totals, NVLink exchange, hand over to the solvers -----
 template <int R>
 __device__ void control_reduce(const KParams& p, ControlSmem<R>& cs) {
     constexpr int NSP2 = nstat2_pad(R), NST2 = nstat2(R);
-    const int tid = threadIdx.x - C_SOLVERS, lane = tid & 31, warp = tid >> 5;
-    constexpr int NTHR = 512 - C_SOLVERS, NW = NTHR / 32;
-    const int ndata = p.cps;
-    const int pstr = (ndata + 7) & ~7;
+    const int tid = threadIdx.x - C_SOLVERS;
+    const int NTHR = (int)blockDim.x - C_SOLVERS;
+    const uint4* totals = reinterpret_cast<const uint4*>(p.gparams) + 4 * MAXR;
     for (int64_t t = 0; t < p.n_steps; ++t) {
         const int b = (int)(t & 1);
         double* tot2 = cs.tot2[b];
-        if (t >= 2) named_bar_sync(CB_EMPTY + b, 512);             // the solvers are done with the sums of step t-2
+        if (t >= 2) named_bar_sync(CB_EMPTY + b, (int)blockDim.x);   // the solvers are done with the sums of step t-2
         stamp(p, t, 2, C_SOLVERS);
-        if (tid == 0) {
-            const unsigned long long target = (unsigned long long)ndata * (unsigned long long)(t / 2 + 1);
-            while (ld_acquire_gpu(p.bar + b) < target) {
-            }
-        }
-        __syncwarp();
-        stamp(p, t, 3, C_SOLVERS);
+        for (int e = tid; e < NST2; e += NTHR) tot2[e] = cell_poll(totals + (size_t)b * NSP2 + e, (uint32_t)(t + 1));
         sync_n<CB_R>(NTHR);
-        // deterministic sum of the CTA partials [entry][cta]: one warp per entry, 4 entries in flight, lanes over
-        // pairs of CTAs (16-byte coalesced loads), fixed in-lane order and a fixed xor tree across the lanes
-        {
-            const double* base = p.partials + (size_t)b * NSP2 * pstr;
-            constexpr int EB = 4;
-            for (int e0 = warp; e0 < NST2; e0 += NW * EB) {
-                double2 v[EB][4];
-                // unconditional loads from clamped addresses (all EB * 4 in flight), masked afterwards
-#pragma unroll
-                for (int q = 0; q < EB; ++q) {
-                    const int e = min(e0 + NW * q, NST2 - 1);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = min(2 * (lane + 32 * j), pstr - 2);
-                        v[q][j] = __ldcg(reinterpret_cast<const double2*>(base + (size_t)e * pstr + c));
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < EB; ++q) {
-                    const int e = e0 + NW * q;
-                    double h[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = 2 * (lane + 32 * j);
-                        h[j] = (c < ndata ? v[q][j].x : 0.0) + (c + 1 < ndata ? v[q][j].y : 0.0);
-                    }
-                    const double sum = warp_allsum((h[0] + h[1]) + (h[2] + h[3]));
-                    if (lane == 0 && e < NST2) tot2[e] = sum;
-                }
-            }
-            sync_n<CB_R>(NTHR);
-        }
         stamp(p, t, 4, C_SOLVERS);
         if (p.world > 1) gpu_exchange<NST2, NSP2, CB_R>(p, tot2, cs.tmp2, tid, t, 0, NTHR);
         stamp(p, t, 13, C_SOLVERS);
         __threadfence_block();
-        named_bar_arrive(CB_FULL + b, 512);
+        named_bar_arrive(CB_FULL + b, (int)blockDim.x);
     }
 }
 
@@ -551,7 +554,7 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
         const int b = (int)(t & 1);
         const double* t2 = cs.tot2[b];
         stamp(p, t, 0);
-        named_bar_sync(CB_FULL + b, 512);
+        named_bar_sync(CB_FULL + b, (int)blockDim.x);
         stamp(p, t, 1);
         // (A) A_t = A0 + u g' + g u' + kappa g g' (packed upper triangle), h_t = h0 + psi g, scalars
         {
@@ -570,7 +573,7 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
             if (tid < 3) a2[NGm + R + tid] = t2[NGm + 2 * R + 2 + tid];     // gamma, q0, n_obs
         }
         sync_n<CB_S>(NTHR);
-        named_bar_arrive(CB_EMPTY + b, 512);                        // cs.tot2[b] may be refilled (step t+2)
+        named_bar_arrive(CB_EMPTY + b, (int)blockDim.x);                        // cs.tot2[b] may be refilled (step t+2)
         // (B) augmented matrix [I + Pbar G | Pbar], G = w1 A_t
         if (!simp) {
             const double w1 = sh.w1;
@@ -784,6 +787,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     // a CTA is either the control CTA or a data CTA: their static shared state shares one buffer
     constexpr size_t SBYTES = sizeof(ControlSmem<R>) > sizeof(DataSmem<R>) ? sizeof(ControlSmem<R>) : sizeof(DataSmem<R>);
     __shared__ __align__(16) unsigned char static_smem[SBYTES];
+    extern __shared__ __align__(128) unsigned char dyn_smem_s[];
     if (blockIdx.x == gridDim.x - 1) {       // ---- control CTA ----
         ControlSmem<R>& cs = *reinterpret_cast<ControlSmem<R>*>(static_smem);
         if (threadIdx.x < C_SOLVERS) control_solve<R>(p, cs);
@@ -792,7 +796,6 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     }
     using L = SlotLayout<R, T>;
     const int NPW = p.npw;                                         // active pass warps (<= V2_PASS_WARPS)
-    extern __shared__ __align__(128) unsigned char dyn_smem_s[];
     DataSmem<R>& ps = *reinterpret_cast<DataSmem<R>*>(static_smem);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -815,14 +818,18 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
         }
         mbar_init(&ps.par_full[0], 1);
         mbar_init(&ps.par_full[1], 1);
-        ps.arrived = 0;
-        ps.sum_done = 0;
+        mbar_init(&ps.red_full, (uint32_t)p.npw);
+        mbar_init(&ps.red_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < nt * TILE; i += blockDim.x) ebuf[i] = 0.0;
     __syncthreads();
 
-    if (warp == V2_PASS_WARPS) {             // ---- producer warp ----
+    if (warp == V2_PASS_WARPS) {             // ---- reduce warp ----
+        reduce_warp<R>(p, ps, lane, p.npw);
+        return;
+    }
+    if (warp == V2_PASS_WARPS + 1) {         // ---- producer warp ----
         if (lane == 0) s_producer<R, T>(p, ps, slots, Cs, tb, nt, nslot);
         return;
     }
@@ -832,6 +839,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     if (wp >= NPW) return;
     const T* Yb = reinterpret_cast<const T*>(p.Y);
     const uint8_t* Mb = p.M;
+    YM<T> nx = load_ym<T>(p, Yb, Mb, 0, (int64_t)(tb + wp) * TILE + lane, false, true);
     for (int64_t pass = 0; pass < n; ++pass) {
         if (wp == 0 && lane == 0) stamp_pass(p, pass, 11, 0, true);
         if (pass >= 1) fetch_params<R>(p, ps, pass - 1, wp, lane);   // {g_{pass-2}, xbar_{pass-1}}
@@ -844,9 +852,8 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
             }
         }
         T* Yrec_prev = (p.Yrec && pass >= 1) ? reinterpret_cast<T*>(p.Yrec) + (pass - 1) * p.ldrec : nullptr;
-        s_warp_pass<R, T, false>(p, ps, ebuf, slots, Yrec_prev, Yb, Mb, tb, nt, nslot, pass, wp, lane, NPW);
+        s_warp_pass<R, T, false>(p, ps, ebuf, slots, Yrec_prev, Yb, Mb, tb, nt, nslot, pass, wp, lane, NPW, nx);
         if (wp == 0 && lane == 0) {
-            stamp_pass(p, pass, 9, 0, true);
             if (p.trace != nullptr && pass < p.trace_steps) {      // per-CTA pass end times behind the 16-entry rows
                 unsigned long long v;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
@@ -859,7 +866,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     fetch_params<R>(p, ps, n, wp, lane);
     {
         T* Yrec_prev = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (n - 1) * p.ldrec : nullptr;
-        s_warp_pass<R, T, true>(p, ps, ebuf, slots, Yrec_prev, Yb, Mb, tb, nt, nslot, n, wp, lane, NPW);
+        s_warp_pass<R, T, true>(p, ps, ebuf, slots, Yrec_prev, Yb, Mb, tb, nt, nslot, n, wp, lane, NPW, nx);
     }
 }
 

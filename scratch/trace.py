@@ -19,13 +19,14 @@ per_cta_start = raw[T * 176:].reshape(160, T)
 us = lambda a: a.mean() / 1e3
 print("d=%d kernel=%d  step mean %.2f us" % (d, kernel, us(t[1:, 0] - t[:-1, 0])))
 if kernel == 2:
-    print("  reducers: wait for arrivals %.2f | sum partials %.2f | exchange %.2f" % (us(t[:, 3] - t[:, 2]), us(t[:, 4] - t[:, 3]), us(t[:, 13] - t[:, 4])))
+    print("  control reducers: poll totals %.2f | exchange %.2f" % (us(t[:, 4] - t[:, 2]), us(t[:, 13] - t[:, 4])))
     print("  solvers: wait for stats %.2f | assemble+fill+eliminate %.2f | x, publish %.2f | rest of update + predict %.2f   (critical: stats->publish %.2f)"
           % (us(t[:, 1] - t[:, 0]), us(t[:, 7] - t[:, 1]), us(t[:, 6] - t[:, 7]), us(t[:, 12] - t[:, 6]), us(t[:, 6] - t[:, 1])))
-    print("  chain: arrivals seen -> stats ready %.2f -> published %.2f ; publish(t) -> arrivals(t+2) seen %.2f"
-          % (us(t[:, 13] - t[:, 3]), us(t[:, 6] - t[:, 13]), us(t[2:, 3] - t[:-2, 6])))
-    print("  pass warp 0: pass %.2f us, wait for params %.2f us, waiting for slots %.2f us"
-          % (us(t[:, 9] - t[:, 8]), us(t[:, 8] - t[:, 11]), t[:, 10].mean() / 1.9e3))
+    print("  chain: CTA 0 released -> stats ready %.2f -> published %.2f ; publish(t) -> CTA 0 released (t+2) %.2f"
+          % (us(t[:, 13] - t[:, 9]), us(t[:, 6] - t[:, 13]), us(t[2:, 9] - t[:-2, 6])))
+    print("  pass warp 0: start -> CTA partial released %.2f us (tiles %.2f | write sums %.2f | reduce warp: CTA sum, store, release %.2f), wait for params %.2f us, waiting for slots %.2f us"
+          % (us(t[:, 9] - t[:, 8]), us(t[:, 14] - t[:, 8]), us(t[:, 15] - t[:, 14]), us(t[:, 9] - t[:, 15]), us(t[:, 8] - t[:, 11]), t[:, 10].mean() / 1.9e3))
+    print("  data CTA 0: params seen - published %.2f" % (us(t[2:, 8] - t[:-2, 6])))
 else:
     print("  pass %.2f | partial+barrier+reduce %.2f | solve %.2f" % (us(t[:, 1] - t[:, 0]), us(t[:, 5] - t[:, 1]), us(t[:, 6] - t[:, 5])))
 
@@ -60,6 +61,6 @@ if kernel == 2:
     for k in range(20, 28):
         kk = k + 20
         print("   step %d: ctrl %7.1f %7.1f %7.1f %7.1f | cta0 %7.1f %7.1f | ctaZ %7.1f %7.1f | ends %7.1f %7.1f" % (
-            kk, (t[k,2]-t0)/1e3, (t[k,3]-t0)/1e3, (t[k,13]-t0)/1e3, (t[k,6]-t0)/1e3,
+            kk, (t[k,2]-t0)/1e3, (t[k,4]-t0)/1e3, (t[k,13]-t0)/1e3, (t[k,6]-t0)/1e3,
             (per_cta_start[0,kk]-t0)/1e3, (per_cta[0,kk]-t0)/1e3, (per_cta_start[z,kk]-t0)/1e3, (per_cta[z,kk]-t0)/1e3,
             (per_cta[:nc,kk].min()-t0)/1e3, (per_cta[:nc,kk].max()-t0)/1e3))
