@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--d", type=int, default=1_000_000)
+    ap.add_argument("--d", "--rows", dest="d", type=int, default=1_000_000, help="rows of C (--rows: torchrun's parser trips over --d)")
     ap.add_argument("--r", type=int, default=16)
     ap.add_argument("--T", type=int, default=10_000, help="length of the resident synthetic sequence")
     ap.add_argument("--window", type=int, default=500, help="filter steps per kernel launch (= per bench step)")
@@ -139,6 +139,7 @@ def cpu_reference_sample(d, r, nsteps, Yh, Mh, C0h, x0h):
     init = init_state(r)
     from oracle import psmf_oracle_c as pc
     if pc.available():
+        pc.use_all_cores()
         pc.run(C0h[:1024], x0h, init["P"], init["V"], init["Q"], init["rho"], init["lam"], Yh[:2, :1024], Mh[:2, :1024])
         Cc = np.ascontiguousarray(C0h, dtype=np.float64)
         Yc = np.ascontiguousarray(Yh[:nsteps], dtype=np.float64)
@@ -290,12 +291,12 @@ def main():
         del Yh, Mh
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:                      # reported at N = 1 only
         ns = args.cpu_steps or max(8, min(400, int(300e6 / max(d, 1))))     # ~10-20 s of host work at d = 1M
         ns = min(ns, T)
         v, threads, what = cpu_reference_sample(d_loc, r, ns, Y[:ns].double().cpu().numpy(), M[:ns].cpu().numpy(),
                                                 C0.cpu().numpy(), x0.numpy())
-        cpu = dict(value=v * (d_loc / d) if world > 1 else v, unit="filter steps/s", cores=threads, kind="port",
+        cpu = dict(value=v, unit="filter steps/s", cores=threads, kind="port",
                    sample="%d filter steps of the same workload prefix (d=%d rows, r=%d) through %s; the reference's "
                           "d x d form cannot run at d=1M" % (ns, d_loc, r, what))
 
@@ -338,7 +339,7 @@ def run_reference(args):
     init = init_state(r)
     from oracle import psmf_oracle_c as pc
     if pc.available():
-        threads = pc.threads()
+        threads = pc.use_all_cores()
         what = "oracle/psmf_oracle_c.c (C/OpenMP port, %d threads)" % threads
         st = dict(C=C0, x=x0, P=init["P"], V=init["V"], Q=init["Q"], rho=init["rho"], lam=init["lam"])
 

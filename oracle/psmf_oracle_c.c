@@ -19,6 +19,15 @@
 
 #define MAXR 16
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU baseline sets its thread count explicitly */
+void psmf_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int psmf_oracle_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -27,6 +27,17 @@ def threads():
     return int(_lib().psmf_oracle_threads())
 
 
+def use_all_cores():
+    """Use every core this process may run on (torchrun exports OMP_NUM_THREADS=1); returns the thread count."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    L = _lib()
+    L.psmf_oracle_set_threads(C.c_int(n))
+    return int(L.psmf_oracle_threads())
+
+
 def run(C_, x, P, V, Q, rho, lam, Y, M, robust=True, cupdate_vt=True, want_X=True):
     """Arrays are copied; returns dict(C, x, P, V, Q, rho, lam, X, bad)."""
     L = _lib()

@@ -83,7 +83,7 @@ struct psmf_engine {
     int last_kernel = 0;
     unsigned long long* trace = nullptr;
     int trace_steps = 0;
-    // NVLink mailbox (world_size > 1): [2][MAX_PEERS][nstat_pad] doubles followed by [2][MAX_PEERS] flags
+    // NVLink mailbox (world_size > 1): [2 parities][MAX_PEERS][192] tagged 16-byte cells (psmf_filter.cuh gpu_exchange)
     void* mbox = nullptr;
     void* peer_mbox[PSMF_MAX_PEERS] = {nullptr};
     bool connected = false;
@@ -94,8 +94,7 @@ struct psmf_engine {
 
 static std::string g_create_error;
 
-static size_t mbox_data_bytes() { return (size_t)2 * PSMF_MAX_PEERS * 192 * sizeof(double); }   // slots of <= nstat2_pad(16) = 176 doubles
-static size_t mbox_bytes() { return mbox_data_bytes() + (size_t)2 * PSMF_MAX_PEERS * sizeof(unsigned long long); }
+static size_t mbox_bytes() { return (size_t)2 * PSMF_MAX_PEERS * 192 * 16; }   // slots of <= nstat2_pad(16) = 176 cells
 
 static int fail(psmf_engine* h, int code, const std::string& msg) {
     if (h)
@@ -368,10 +367,8 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
         if (!h->connected) return fail(h, PSMF_E_STATE, "world_size > 1: call psmf_mailbox_connect before psmf_run");
         // the mailbox slots are nstat_pad(R) doubles apart (kernel indexing), inside a buffer sized for MAXR
         p.mbox_local = (double*)h->mbox;
-        p.flag_local = (unsigned long long*)((char*)h->mbox + mbox_data_bytes());
         for (int i = 0; i < p.world; ++i) {
             p.mbox_peer[i] = (double*)h->peer_mbox[i];
-            p.flag_peer[i] = (unsigned long long*)((char*)h->peer_mbox[i] + mbox_data_bytes());
         }
         p.step_base = h->step_base;
     }
@@ -392,9 +389,10 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
         p.cps = h->cps2;
         p.nslot = h->nslot;
         p.trace_cta = h->cps2;
-        // streaming from HBM: fewer pass warps keep up with the ring and leave issue slots to the producer (measured
-        // optimum 11 of 15 at r = 16); resident in shared memory: every warp helps
-        p.npw = h->resident2 ? V2_CWARPS : (V2_CWARPS * 3 + 3) / 4;
+        // streaming from HBM: 12 of the 14 pass warps (3 per scheduler; a multiple of the 4 tiles of a chunk) keep up
+        // with the ring and leave issue slots to the producer -- measured optimum at r = 16 under the power cap;
+        // resident in shared memory: every warp helps
+        p.npw = h->resident2 ? V2_CWARPS : 12;
         if (const char* ev = getenv("PSMF_NPW")) { const int v = atoi(ev); if (v >= 1 && v <= V2_CWARPS) p.npw = v; }
         p.gparams = h->gparams;
         CK(h, LAUNCH_S[h->R](p, h->cfg.dtype, h->cps2 + 1, h->dyn_smem2, st, true));

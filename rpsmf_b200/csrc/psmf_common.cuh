@@ -80,10 +80,8 @@ struct KParams {
     double alpha, beta;
     // multi-GPU stats exchange
     int32_t world, rank;
-    double* mbox_local;                    // [2][world][nstat_pad] + flags
+    double* mbox_local;                    // NVLink mailbox: [2 parities][MAX_PEERS][192] tagged 16-byte cells
     double* mbox_peer[MAX_PEERS];
-    unsigned long long* flag_local;        // [2][world]
-    unsigned long long* flag_peer[MAX_PEERS];
     unsigned long long step_base;
     // streaming kernel
     int32_t nslot;            // shared-memory chunk slots per CTA

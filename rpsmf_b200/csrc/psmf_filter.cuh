@@ -75,6 +75,32 @@ __device__ __forceinline__ void red_release_gpu(unsigned long long* p, unsigned 
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Tagged 16-byte cells {lo, tag, hi, tag}: a double that carries its own "valid for step tag" mark in each
+// 8-byte half (the layout of NCCL's LL protocol), so a reader polls the data itself -- one memory round trip,
+// no separate flag, no fence on the writer side, and a torn 16-byte access can never be taken for valid.
+__device__ __forceinline__ void cell_store(uint4* cell, double v, uint32_t tag) {
+    const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __forceinline__ double cell_poll(const uint4* cell, uint32_t tag) {
+    uint32_t lo, t0, hi, t1;
+    do {
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(cell) : "memory");
+    } while (t0 != tag || t1 != tag);
+    return __hiloint2double((int)hi, (int)lo);
+}
+__device__ __forceinline__ void cell_store_sys(uint4* cell, double v, uint32_t tag) {      // peer GPU over NVLink
+    const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __forceinline__ double cell_poll_sys(const uint4* cell, uint32_t tag) {
+    uint32_t lo, t0, hi, t1;
+    do {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(cell) : "memory");
+    } while (t0 != tag || t1 != tag);
+    return __hiloint2double((int)hi, (int)lo);
+}
+
 // barrier 0 over the first `n` threads of the CTA (n == blockDim.x: plain __syncthreads; the streaming
 // kernel excludes its producer warp)
 template <int BAR = 0>
@@ -480,42 +506,32 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
 
 // ---- cross-GPU exchange of the (already grid-reduced) statistics over NVLink -------------------------------
 // Rows of C are sharded over `world` GPUs; V, P, Q, x, lambda are replicated.  Per step every GPU needs
-// the sum over all shards of nstat(R) doubles (1.2 kB at r = 16).  CTA 0 of each GPU stores its local
-// totals into slot [parity][rank] of every peer's mailbox with plain peer stores (NVLink P2P) and then
-// releases a per-source flag (system scope); every CTA of every GPU polls its LOCAL flags, then adds the
-// world slots in rank order -- the same order on every GPU, so the replicated state stays bit-identical.
-// Two parities make the mailbox safe without a second handshake: a GPU can only be one step ahead of its
-// slowest peer (it needs that peer's flag of the current step to proceed).
+// the sum over all shards of the statistics vector (1.4 kB at r = 16).  One CTA of each GPU (part == 0) stores
+// its local totals as tagged cells into slot [parity][rank] of every peer's mailbox with plain peer stores
+// (NVLink P2P); every CTA polls the cells of its LOCAL mailbox and adds the world slots in rank order -- the
+// same order on every GPU, so the replicated state stays bit-identical.  No fence and no flag: the latency
+// is one NVLink store plus one local poll.  Two parities make the mailbox safe without a handshake: a GPU
+// can only be one step ahead of its slowest peer (it needs that peer's cells of the current step to proceed).
 template <int NST, int NSP, int BAR = 0>
-__device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restrict__ tot, double* __restrict__ tmp, int tid,
+__device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restrict__ tot, double* __restrict__ /*tmp*/, int tid,
                                              int64_t t, int part, int nthr) {
-    const int parity = (int)((p.step_base + (unsigned long long)t) & 1ULL);
-    const unsigned long long target = p.step_base + (unsigned long long)t + 1ULL;
+    const unsigned long long step = p.step_base + (unsigned long long)t;
+    const int parity = (int)(step & 1ULL);
+    const uint32_t tag = (uint32_t)(step + 1ULL);
     if (part == 0) {
         for (int e = tid; e < NST; e += nthr) {
             const double v = tot[e];
             for (int pr = 0; pr < p.world; ++pr)
-                if (pr != p.rank) st_relaxed_sys_f64(p.mbox_peer[pr] + ((size_t)parity * MAX_PEERS + p.rank) * NSP + e, v);
-        }
-        __threadfence_system();
-        sync_n<BAR>(nthr);
-        if (tid < p.world && tid != p.rank)
-            st_release_sys(p.flag_peer[tid] + parity * MAX_PEERS + p.rank, target);
-    }
-    if (tid < p.world && tid != p.rank) {
-        const unsigned long long* f = p.flag_local + parity * MAX_PEERS + tid;
-        while (ld_acquire_sys(f) < target) {
+                if (pr != p.rank)
+                    cell_store_sys(reinterpret_cast<uint4*>(p.mbox_peer[pr]) + ((size_t)parity * MAX_PEERS + p.rank) * NSP + e, v, tag);
         }
     }
-    sync_n<BAR>(nthr);
+    const uint4* local = reinterpret_cast<const uint4*>(p.mbox_local) + (size_t)parity * MAX_PEERS * NSP;
     for (int e = tid; e < NST; e += nthr) {
         double s = 0.0;
-        for (int src = 0; src < p.world; ++src)
-            s += (src == p.rank) ? tot[e] : ld_relaxed_sys_f64(p.mbox_local + ((size_t)parity * MAX_PEERS + src) * NSP + e);
-        tmp[e] = s;
+        for (int src = 0; src < p.world; ++src) s += (src == p.rank) ? tot[e] : cell_poll_sys(local + (size_t)src * NSP + e, tag);
+        tot[e] = s;                                              // entry e is read and written by this thread only
     }
-    sync_n<BAR>(nthr);
-    for (int e = tid; e < NST; e += nthr) tot[e] = tmp[e];
     sync_n<BAR>(nthr);
 }
 

@@ -394,18 +394,6 @@ __device__ void s_producer(const KParams& p, DataSmem<R>& ps, unsigned char* slo
 // One 16-byte cell per double, {lo, tag, hi, tag} with tag = s + 1: every 8-byte half carries its own tag, so
 // a reader that polls the cell needs no separate flag (one L2 round trip instead of two) and never sees a torn
 // value.  p.gparams = [2 parities][2R] cells, zeroed by the host before every launch.
-__device__ __forceinline__ void cell_store(uint4* cell, double v, uint32_t tag) {
-    const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
-}
-__device__ __forceinline__ double cell_poll(const uint4* cell, uint32_t tag) {
-    uint32_t lo, t0, hi, t1;
-    do {
-        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(cell) : "memory");
-    } while (t0 != tag || t1 != tag);
-    return __hiloint2double((int)hi, (int)lo);
-}
-
 // named barriers of the control CTA
 constexpr int CB_GJ = 1;           // elimination threads
 constexpr int CB_S = 2;            // solver group
