@@ -7,15 +7,19 @@
 //                SASS) that complete on mbarriers, and bulk-stores updated chunks back.
 //                   streaming (chunks of the CTA > slots): ring, every chunk loaded and stored once per step;
 //                   resident  (chunks <= slots): C is loaded once and stays in shared memory for the launch.
-//                15 pass warps: one warp per 32-row tile, all warps independent (lane = row for the rank-1
-//                update / y_hat / e, fp64 DMMA fragments for the Gram-type sums); the last warp to finish a pass
-//                adds the 15 per-warp partials in fixed order, writes the CTA partial to global memory and
-//                bumps a global arrival counter.
-//   control CTA  waits for the arrival counter, adds the CTA partials in fixed order (deterministic), exchanges
-//                with the other GPUs over NVLink, runs the r x r solve with all its threads and publishes
-//                {g_t, xbar_{t+1}} + a flag in global memory.  It is the only CTA that holds V, P, Q, x, lambda.
-//                A dedicated SM keeps the latency-bound solve away from the DMMA traffic of the pass warps
-//                (measured: 3 us alone vs 8-23 us when it shared an SM with them) and removes every grid barrier.
+//                14 pass warps (12 used when streaming): one warp per 32-row tile, all warps independent (lane =
+//                row for the rank-1 update / y_hat / e, fp64 DMMA fragments for the Gram-type sums); at the end
+//                of a pass a warp leaves its sums in shared memory, arrives on an mbarrier and moves on.
+//                reduce warp: adds the per-warp sums in fixed order, writes the CTA partial to global memory
+//                and bumps a global arrival counter; once all CTAs have arrived it sums ITS share of the
+//                entries over all CTAs (fixed order: deterministic) and publishes the totals as tagged cells.
+//                (One SM ingests only ~40 GB/s: a single CTA summing the ~200 kB of partials costs >= 5 us.)
+//   control CTA  warps 8-15 poll the totals, exchange them with the other GPUs over NVLink and hand them to
+//                warps 0-7, which run the r x r solve and publish {g_t, xbar_{t+1}} as tagged cells as soon as
+//                x_t exists; the rest of the update follows off the critical path.  It is the only CTA that
+//                holds V, P, Q, x, lambda.  A dedicated SM keeps the latency-bound solve away from the DMMA
+//                traffic of the pass warps (measured: 3 us alone vs 8-23 us when it shared an SM with them)
+//                and there is no grid barrier anywhere.
 //
 // Software pipeline.  The statistics of step t are sums over C_t = C_{t-1} + e_{t-1} g_{t-1}', and g_{t-1}
 // only exists after the solve of step t-1.  Expanding the rank-1 term,
@@ -29,12 +33,12 @@
 // step t-1.  So pass P_t (which turns C_{t-2} in HBM into C_{t-1}, computes e_{t-1} and the sums for step t)
 // only needs the solve of step t-2 and runs CONCURRENTLY with the reduction / solve of step t-1; the solve of
 // step t assembles A_t, bu_t, q1_t from the reduced sums in O(r^2) and proceeds as in psmf_filter.cuh.  The
-// step time becomes max(pass, (pass + reduce + solve) / 2) instead of pass + reduce + solve.  One extra
+// step time becomes max(pass, (pass + reduce + solve) / 2) instead of pass + reduce + solve (two steps in flight).  One extra
 // read of y_t / m_t per step (+3 % HBM bytes) pays for it; C is still read and written once per step.
 //
 // Parameter sets: set s = {g_{s-1}, xbar_s} (set 0 = {0, xbar_0} from the state entering the launch); pass p
 // needs set p-1, the flush pass n needs sets n-1 and n.  The control CTA publishes set t+1 after the solve
-// of step t at gparams[(t+1) & 1] and then stores flag = t+2.
+// of step t as tagged cells (tag t+2) at gparams[(t+1) & 1].
 //
 // Requirements checked by the host (else the direct-load kernel of psmf_filter.cuh is used): one series,
 // d a multiple of 16, at least two SMs.
