@@ -129,7 +129,7 @@ struct DataSmem {
 // per-warp accumulators of one pipelined pass
 struct PassAcc {
     double g00[2], g01[2], g11[2];   // fragments of A0 = sum m_t c c'
-    double u0[2], u1[2];             // fragments of [u | h0] for columns 0..7 / 8..15 of C
+    double u0[2], u1[2];             // per-lane partial sums {u, h0} of column lane/4 (u0) and 8 + lane/4 (u1) over rows = lane%4 mod 4
     double v[5];                     // per-lane: kappa, psi, gamma, q0, n_obs
     __device__ __forceinline__ void zero() {
         g00[0] = g00[1] = g01[0] = g01[1] = g11[0] = g11[1] = u0[0] = u0[1] = u1[0] = u1[1] = 0.0;
@@ -257,16 +257,19 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
                 const int pos = r4 ^ (mm << 2);
                 const double a0 = (mm < R) ? (double)tile[mm * 32 + pos] : 0.0;
                 const double b0 = mrow ? a0 : 0.0;
+                // [u | h0]: plain FMAs on the element this lane holds anyway (an 8x8x4 DMMA would waste 6 of its 8
+                // columns: 16 fp64-pipe cycles against 2 per FMA)
                 const double se = __shfl_sync(FULL, me, r4), sy = __shfl_sync(FULL, my, r4);
-                const double bx = (mm == 0) ? se : ((mm == 1) ? sy : 0.0);
                 dmma884(acc.g00, a0, b0);
-                dmma884(acc.u0, a0, bx);
+                acc.u0[0] = fma(a0, se, acc.u0[0]);
+                acc.u0[1] = fma(a0, sy, acc.u0[1]);
                 if constexpr (R > 8) {
                     const double a1 = (8 + mm < R) ? (double)tile[(8 + mm) * 32 + pos] : 0.0;
                     const double b1 = mrow ? a1 : 0.0;
                     dmma884(acc.g01, a0, b1);
                     dmma884(acc.g11, a1, b1);
-                    dmma884(acc.u1, a1, bx);
+                    acc.u1[0] = fma(a1, se, acc.u1[0]);
+                    acc.u1[1] = fma(a1, sy, acc.u1[1]);
                 }
             }
         }
@@ -302,7 +305,16 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
                 if (mm <= n && 8 + n < R) r0[gram_off(R, 8 + mm) + (n - mm)] = acc.g11[x];
             }
         }
-        if (kq == 0) {                                             // D[mm][0] = u_mm, D[mm][1] = h0_mm
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {                          // sum over the four row classes kq (fixed order)
+            acc.u0[0] += __shfl_xor_sync(FULL, acc.u0[0], o);
+            acc.u0[1] += __shfl_xor_sync(FULL, acc.u0[1], o);
+            if constexpr (R > 8) {
+                acc.u1[0] += __shfl_xor_sync(FULL, acc.u1[0], o);
+                acc.u1[1] += __shfl_xor_sync(FULL, acc.u1[1], o);
+            }
+        }
+        if (kq == 0) {                                             // u_mm, h0_mm
             if (mm < R) {
                 r0[ngram(R) + mm] = acc.u0[0];
                 r0[ngram(R) + R + mm] = acc.u0[1];
