@@ -254,7 +254,10 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     {
         const int cmax = e->cps > e->cps2 ? e->cps : e->cps2;
         const size_t pstr = (size_t)((cmax + 7) & ~7) + 1;            // transposed partials + totals (grid_reduce)
-        CKC(cudaMalloc(&e->partials, (size_t)2 * nsp * (pstr > 17 ? pstr : 17) * sizeof(double)));   // also >= 2 * cps2 * nstat2_pad
+        // direct kernel: doubles; pipelined kernel: [2][nstat2_pad][pstr] tagged 16-byte cells
+        const size_t pbytes = (size_t)2 * nsp * (pstr > 17 ? pstr : 17) * 16;
+        CKC(cudaMalloc(&e->partials, pbytes));
+        CKC(cudaMemset(e->partials, 0, pbytes));
     }
     CKC(cudaMalloc(&e->bar, 8 * sizeof(unsigned long long)));
     CKC(cudaMalloc(&e->gparams, GPARAMS_BYTES));                        // 16-byte cells (psmf_stream.cuh): parameter sets [2][2R], totals [2][nstat2_pad]
@@ -370,8 +373,8 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
         for (int i = 0; i < p.world; ++i) {
             p.mbox_peer[i] = (double*)h->peer_mbox[i];
         }
-        p.step_base = h->step_base;
     }
+    p.step_base = h->step_base;       // steps filtered by this engine so far: tags of the mailbox / partial cells
     p.trace = h->trace; p.trace_steps = h->trace_steps;
     CK(h, cudaMemsetAsync(h->bar, 0, 8 * sizeof(unsigned long long), st));
     CK(h, cudaMemsetAsync(h->gparams, 0, GPARAMS_BYTES, st));

@@ -70,7 +70,7 @@ struct KParams {
     double* scal_out;
     const double* xbar_ext; const double* F_ext;
     double* grad_out;         // (n_series, R) accumulated theta gradient or nullptr
-    double* partials;         // direct kernel: grid_reduce scratch; pipelined kernel: [2][cps][nstat2_pad]
+    double* partials;         // direct kernel: grid_reduce scratch; pipelined kernel: [2][nstat2_pad][pstr] tagged cells
     unsigned long long* bar;  // direct kernel: grid barrier counter; pipelined kernel: [0..1] arrival counters, [2] flag
     long long* status;        // first bad step or -1
     int64_t d, d_global;

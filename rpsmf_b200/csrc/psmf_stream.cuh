@@ -442,10 +442,13 @@ __device__ void reduce_warp(const KParams& p, DataSmem<R>& ps, int lane, int NPW
     constexpr int NE = (NST2 + 31) / 32;
     const int ndata = p.cps, pstr = (ndata + 7) & ~7, cta = blockIdx.x;
     uint4* totals = reinterpret_cast<uint4*>(p.gparams) + 4 * MAXR;
+    uint4* pcells = reinterpret_cast<uint4*>(p.partials);
     for (int64_t t = 0; t < p.n_steps; ++t) {
         const int b = (int)(t & 1);
-        double* base = p.partials + (size_t)b * NSP2 * pstr;
-        // (1) CTA partial of pass t: per-warp sums in fixed warp order -> global [parity][entry][cta]
+        // the partial cells outlive the launch: their tags count the steps of the engine, not of the launch
+        const uint32_t ptag = (uint32_t)(p.step_base + (unsigned long long)t + 1ULL);
+        uint4* base = pcells + (size_t)b * NSP2 * pstr;
+        // (1) CTA partial of pass t: per-warp sums in fixed warp order -> tagged cells [parity][entry][cta]
         mbar_wait(&ps.red_full, (uint32_t)b);
         {
             double sum[NE];
@@ -459,33 +462,31 @@ __device__ void reduce_warp(const KParams& p, DataSmem<R>& ps, int lane, int NPW
             if (lane == 0) mbar_arrive(&ps.red_free);
 #pragma unroll
             for (int i = 0; i < NE; ++i)
-                if (lane + 32 * i < NST2) base[(size_t)(lane + 32 * i) * pstr + cta] = sum[i];
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                red_release_gpu(p.bar + b, 1ULL);
-                stamp_pass(p, t, 9, 0, true);
-            }
+                if (lane + 32 * i < NST2) cell_store(base + (size_t)(lane + 32 * i) * pstr + cta, sum[i], ptag);
+            if (lane == 0) stamp_pass(p, t, 9, 0, true);
             __syncwarp();
         }
-        // (2) this CTA's share of the grid reduction: entries cta, cta + ndata, .. summed over all CTAs
-        if (cta < NST2) {
-            if (lane == 0) {
-                const unsigned long long target = (unsigned long long)ndata * (unsigned long long)(t / 2 + 1);
-                while (ld_acquire_gpu(p.bar + b) < target) {
+        // (2) this CTA's share of the grid reduction: entries cta, cta + ndata, .. summed over all CTAs.  The warp
+        // polls the cells of one entry together (one L2 round trip per attempt), lanes over the CTAs.
+        for (int e = cta; e < NST2; e += ndata) {
+            const uint4* row = base + (size_t)e * pstr;
+            double v[8];
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = lane + 32 * j;
+                    uint32_t lo, t0, hi, t1;
+                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(row + min(c, pstr - 1)) : "memory");
+                    ok = ok && (c >= ndata || (t0 == ptag && t1 == ptag));
+                    v[j] = (c < ndata) ? __hiloint2double((int)hi, (int)lo) : 0.0;
                 }
-            }
+            } while (!__all_sync(FULL, ok));
+            const double sum = warp_allsum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])));
+            if (lane == 0) cell_store(totals + (size_t)b * NSP2 + e, sum, (uint32_t)(t + 1));
             __syncwarp();
-            for (int e = cta; e < NST2; e += ndata) {
-                double v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __ldcg(base + (size_t)e * pstr + min(lane + 32 * j, pstr - 1));
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = (lane + 32 * j < ndata) ? v[j] : 0.0;
-                const double sum = warp_allsum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])));
-                if (lane == 0) cell_store(totals + (size_t)b * NSP2 + e, sum, (uint32_t)(t + 1));
-                __syncwarp();
-            }
         }
     }
 }
