@@ -361,14 +361,20 @@ __device__ void gauss_jordan_cta(Smem<R>& sh, int tid) {
         const double inv = __shfl_sync(FULL, cinv, pi);
         used |= 1u << pi;
         if (tid == 0) sh.perm[k] = pi;
+        // all pivot-row loads first: the stores below may alias them as far as the compiler can tell, and
+        // interleaving would serialise load -> multiply -> store per column
+        double rp[CPT];
 #pragma unroll
         for (int e = 0; e < CPT; ++e) {
             const int c = q + TPR * e;
-            if (active && c < NC) {
-                const double rpc = sh.aug[cur][pi][c] * inv;
-                own[e] = (i == pi) ? rpc : fma(-aik, rpc, own[e]);
-                sh.aug[nxt][i][c] = own[e];
-            }
+            rp[e] = sh.aug[cur][pi][c < NC ? c : NC - 1];
+        }
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) {
+            const int c = q + TPR * e;
+            const double rpc = rp[e] * inv;
+            own[e] = (i == pi) ? rpc : fma(-aik, rpc, own[e]);
+            if (active && c < NC) sh.aug[nxt][i][c] = own[e];
         }
         named_bar_sync(GJBAR, NGJ);
     }
