@@ -100,6 +100,7 @@ def test_shapes_and_grids(d, ctas):
     (9600, 2, 10, None),
     (4800, 1, 3, None),
     (12000, 0, 12, None),
+    (300000, 0, 16, False),    # full grid (one data CTA per SM), every CTA streams its chunks through the ring
 ])
 def test_tma_kernel(d, ctas, r, resident):
     T = 12
@@ -185,6 +186,34 @@ def test_run_to_run_determinism():
     Y, M, C0, x0 = make_problem(d, r, T, seed=5)
     init = impute_init(r)
     a = _engine_run(d, r, Y, M, C0, x0, init, True)
+    b = _engine_run(d, r, Y, M, C0, x0, init, True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3]["C"], b[3]["C"])
+
+
+def test_full_size_workload_L():
+    """BASELINE.json's headline shape (d = 1M, r = 16, rPSMF, 20 % missing) on a short prefix: the pipelined
+    kernel against the C/OpenMP oracle (itself pinned against the numpy oracle in the CPU suite), plus the
+    size-independent properties: a row that is never observed (y zero-filled) keeps its C row bit-exactly,
+    and two runs are bit-identical."""
+    from oracle import psmf_oracle_c as pc
+    if not pc.available():
+        pytest.skip("oracle/libpsmf_oracle.so not built (python -c 'import __graft_entry__ as g; g.build()')")
+    pc.use_all_cores()
+    d, r, T = 1_000_000, 16, 6
+    Y, M, C0, x0 = make_problem(d, r, T, seed=2026)
+    dead = np.array([0, 31, 32, 4097, 500_000, d - 1])
+    M[:, dead] = 0
+    Y[:, dead] = 0.0
+    init = impute_init(r)
+    a = _engine_run(d, r, Y, M, C0, x0, init, True)
+    assert a[4]["kernel"] == "tma" and a[4]["resident"] is False
+    ref = pc.run(C0, x0, init["P"], init["V"], init["Q"], init["rho"], init["lam"], Y, M, robust=True, cupdate_vt=True)
+    assert ref["bad"] == -1
+    assert relerr(a[0], ref["X"]) < TOL
+    assert relerr(a[3]["C"], ref["C"]) < TOL
+    assert relerr(a[3]["P"], ref["P"]) < TOL and relerr(a[3]["V"], ref["V"]) < TOL
+    assert relerr(a[3]["rho"], ref["rho"]) < TOL and relerr(a[3]["lam"], ref["lam"]) < TOL
+    assert np.array_equal(a[3]["C"][dead], C0[dead])
     b = _engine_run(d, r, Y, M, C0, x0, init, True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[3]["C"], b[3]["C"])
 
