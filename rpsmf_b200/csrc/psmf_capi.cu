@@ -220,7 +220,10 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
                 const int64_t cap = atoll(ev);
                 if (cap >= 2 && nslot > cap) nslot = cap;
             }
-            if (nslot >= (nchunks_max >= 2 ? 2 : 1)) {
+            // a ring needs depth: with fewer than 5 slots the producer cannot keep loads, stores and the pass warps
+            // apart (very large shards, where the residual buffer eats the shared memory) -> direct-load kernel
+            const bool ring_ok = nchunks_max <= nslot || nslot >= 5;
+            if (ring_ok && nslot >= (nchunks_max >= 2 ? 2 : 1)) {
                 e->cps2 = cps2;
                 e->nslot = (int)nslot;
                 e->dyn_smem2 = (size_t)nslot * slot + ebuf;
@@ -233,7 +236,7 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     }
     if (cfg->kernel == 2 && e->cps2 == 0) {
         free_engine(e);
-        return fail(nullptr, PSMF_E_INVALID, "TMA-staged kernel not available for this shape (needs d % 16 == 0 and room for 2 slots)");
+        return fail(nullptr, PSMF_E_INVALID, "TMA-staged kernel not available for this shape (needs d % 16 == 0, one series, and room for a ring of 5 chunk slots)");
     }
 
     const size_t cbytes = (size_t)e->S * e->ntiles * TILE * e->R * e->esize;

@@ -122,6 +122,7 @@ struct DataSmem {
     uint64_t full[MAXSLOT];        // slot loaded            (producer -> pass warps)
     uint64_t done[MAXSLOT];        // slot processed         (pass warps -> producer)
     uint64_t par_full[2];          // par[s & 1] copied from global memory   (pass warp 0 -> pass warps)
+    volatile int gen[MAXSLOT];     // streaming: lap (load count) of the chunk the producer last requested for the slot
     uint64_t red_full;             // all pass warps have written red[]      (pass warps -> reduce warp)
     uint64_t red_free;             // red[] has been read                    (reduce warp -> pass warps)
 };
@@ -195,6 +196,15 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
         const uint32_t parity = (uint32_t)((streaming ? kk / nslot : pass) & 1);
         unsigned char* sb = slots + (size_t)slot * L::SLOT;
         const long long c0 = clock64();
+        // mbarrier waits only know the parity of a phase.  Bulk loads complete out of order, so a warp that jumps
+        // NPW / TS chunks ahead could reach a slot whose PREVIOUS load is still pending and would take that older
+        // phase (same parity as two laps back) for its own.  The producer therefore publishes the lap it has
+        // requested for the slot; once that is ours, the previous phase is complete and the parity is unambiguous.
+        if (streaming) {
+            const int lap = (int)(kk / nslot);
+            while (ps.gen[slot] < lap) {
+            }
+        }
         mbar_wait(&ps.full[slot], parity);
         wait_full += clock64() - c0;
         const int64_t row = (int64_t)(tb + tl) * TILE + lane;
@@ -356,12 +366,12 @@ __device__ void s_producer(const KParams& p, DataSmem<R>& ps, unsigned char* slo
         // as the pass warps release it and its slot is reloaded with chunk j + nslot right after the store has
         // left shared memory.
         const int64_t total = npass * nchunks;
-        const int lag = nchunks - nslot + 1;          // >= 2: store groups issued after the previous version of a chunk
+        const int gap = nchunks - nslot;              // >= 1: store groups committed since the previous version of the chunk loaded next
         int lk = 0;                                   // chunk-in-pass index of the next load
         int64_t lc = 0;                               // global index of the next load
         for (; lc < total && lc < nslot; ++lc) {
             const uint32_t bytes = lk == nchunks - 1 ? last_bytes : full_bytes;
-            mbar_arrive_expect_tx(&ps.full[lc], bytes);
+            mbar_arrive_expect_tx(&ps.full[lc], bytes);                 // ps.gen[lc] = 0 (lap 0) from the CTA prologue
             bulk_load(slots + (size_t)lc * L::SLOT, Cb + (size_t)lk * CHUNK_ELEMS, bytes, &ps.full[lc]);
             if (++lk == nchunks) lk = 0;
         }
@@ -375,9 +385,12 @@ __device__ void s_producer(const KParams& p, DataSmem<R>& ps, unsigned char* slo
             bulk_commit();
             if (lc < total) {
                 bulk_wait_read<0>();                                               // the store has left shared memory
-                // the previous version of the chunk loaded now (one pass ago) was stored `lag` groups ago
-                if (lag >= 8) bulk_wait<8>(); else if (lag >= 4) bulk_wait<4>(); else if (lag >= 2) bulk_wait<2>(); else bulk_wait<0>();
+                // the previous version of the chunk loaded now (one pass ago) was stored `gap` groups ago: it has landed
+                // once at most gap - 1 newer groups are pending
+                if (gap > 8) bulk_wait<8>(); else if (gap > 4) bulk_wait<4>(); else if (gap > 2) bulk_wait<2>(); else if (gap > 1) bulk_wait<1>(); else bulk_wait<0>();
                 const uint32_t bytes = lk == nchunks - 1 ? last_bytes : full_bytes;
+                ps.gen[slot] = (int)(lc / nslot);                                   // lap of the chunk requested now
+                __threadfence_block();
                 mbar_arrive_expect_tx(&ps.full[slot], bytes);
                 bulk_load(sb, Cb + (size_t)lk * CHUNK_ELEMS, bytes, &ps.full[slot]);
                 if (++lk == nchunks) lk = 0;
@@ -824,6 +837,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
         }
         mbar_init(&ps.par_full[0], 1);
         mbar_init(&ps.par_full[1], 1);
+        for (int s2 = 0; s2 < MAXSLOT; ++s2) ps.gen[s2] = 0;
         mbar_init(&ps.red_full, (uint32_t)p.npw);
         mbar_init(&ps.red_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -218,6 +218,23 @@ def test_full_size_workload_L():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[3]["C"], b[3]["C"])
 
 
+@pytest.mark.parametrize("d,kernel", [(2_000_000, "tma"), (3_000_000, "direct")])
+def test_very_large_shards(d, kernel):
+    """Beyond the headline size on one GPU: at d = 2M the ring shrinks to 5 chunk slots; at d = 3M the residual
+    buffer leaves no room for a ring and the engine must pick the direct-load kernel on its own."""
+    from oracle import psmf_oracle_c as pc
+    if not pc.available():
+        pytest.skip("oracle/libpsmf_oracle.so not built")
+    pc.use_all_cores()
+    r, T = 16, 3
+    Y, M, C0, x0 = make_problem(d, r, T, seed=3)
+    init = impute_init(r)
+    a = _engine_run(d, r, Y, M, C0, x0, init, True)
+    assert a[4]["kernel"] == kernel
+    ref = pc.run(C0, x0, init["P"], init["V"], init["Q"], init["rho"], init["lam"], Y, M, robust=True, cupdate_vt=True)
+    assert relerr(a[0], ref["X"]) < TOL and relerr(a[3]["C"], ref["C"]) < TOL and relerr(a[3]["V"], ref["V"]) < TOL
+
+
 def test_fp32_storage():
     torch = _torch()
     d, r, T = 600, 16, 40
