@@ -10,6 +10,7 @@ All arithmetic runs in hand-written sm_100a CUDA (libpsmf_b200.so, C ABI in incl
 """
 
 from .engine import FilterEngine  # noqa: F401
+from .experiment import prepare_missing, run_impute_experiment  # noqa: F401
 from .impute import ProbabilisticSequentialMatrixFactorizer, robust_PSMF  # noqa: F401
 from .psmf import PSMFIter, PSMFIterMissing, PSMFRecursive  # noqa: F401
 from .rpsmf import rPSMFIter, rPSMFIterMissing, rPSMFRecursive  # noqa: F401
