@@ -56,3 +56,26 @@ def test_argument_checks():
         ex.run_impute_experiment(np.zeros((3, 50)), "BPMF", 30, seed=1, fit=lambda *a: None)
     with pytest.raises(TypeError):
         ex.run_impute_experiment(np.zeros((3, 50)), "PSMF", 30, seed=1, fit=lambda *a: None, rank=4)
+
+
+def test_published_pinning_summary():
+    """tests/golden/pin_published.py replayed all 18 published result files whose input CSVs ship with the
+    reference (3 datasets x 3 percentages x 2 methods): inputs of all 100 repeats by hash, results of the first
+    repeats through the oracle.  The summary it wrote is committed; where the reference is present, one file is
+    replayed live."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    s = json.load(open(os.path.join(here, "golden", "published_pinning.json")))
+    assert len(s["files"]) == 18 and s["all_hashes_match"]
+    assert all(f["repeats_hashed"] == 100 and f["repeats_fitted"] >= 2 for f in s["files"])
+    # end-of-fit scalars of the d x d reference against the O(d r^2) oracle: 17 files <= 1.3e-11, sp500 40 % rPSMF 1.25e-9
+    assert s["max_rel_err_error_predict"] < 2e-9 and s["max_rel_err_error_full"] < 2e-9
+    assert s["max_abs_err_inside_sig"] == 0.0
+    ref = "/root/reference/ExperimentImpute"
+    if os.path.exists(os.path.join(ref, "data", "LondonAir_PM25.csv")):
+        pub = json.load(open(os.path.join(ref, "output", "LondonAir_PM25_20_PSMF.json")))
+        Yorig = np.genfromtxt(os.path.join(ref, "data", "LondonAir_PM25.csv"), delimiter=",")
+        out = ex.run_impute_experiment(Yorig, "PSMF", 20, seed=pub["seed"], repeats=1, fit=_oracle_fit(False))
+        assert out["hashes"]["Y"][0] == pub["hashes"]["Y"][0]
+        assert abs(out["results"]["error_full"][0] - pub["results"]["error_full"][0]) / pub["results"]["error_full"][0] < 1e-9
