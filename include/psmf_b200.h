@@ -136,9 +136,9 @@ int  psmf_status(psmf_handle h, int64_t* first_bad_step);
 int  psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* smem_bytes, int32_t* launches);
 int  psmf_launch_info2(psmf_handle h, int32_t* kernel, int32_t* nslot, int32_t* resident);
 
-/* debug: record globaltimer stamps of CTA 0 for the first `steps` filter steps of every following psmf_run
- * into dev_buf ([steps][16] uint64; entries 8.. are stamps of the first pass warp of the pipelined kernel: pass start, pass end, after CTA sync, before grid barrier, after grid
- * barrier, statistics reduced, step end, after the r x r solve).  dev_buf == NULL disables.           */
+/* debug: record globaltimer stamps for the first `steps` filter steps of every following psmf_run into dev_buf
+ * (steps * (16 + 2 * 160) uint64: 16 slots per step for the control CTA and the first pass warp of data CTA 0, then
+ * per-CTA pass end / start times; scratch/trace.py decodes them).  dev_buf == NULL disables.           */
 int  psmf_set_trace(psmf_handle h, uint64_t* dev_buf, int32_t steps);
 
 /* multi-GPU row sharding (world_size > 1): NVLink mailbox for the per-step statistics exchange.

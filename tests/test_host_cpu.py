@@ -119,3 +119,28 @@ def test_adam_and_learning_rates():
     assert np.allclose(o._theta[1], np.array([[0.49], [0.21]]), atol=1e-9)
     o.optim = "sgd"; o.sgd_init(gam=0.1); o.sgd_update(2)
     assert np.allclose(o._theta[2], np.maximum(o._theta[1] - 0.1 * o._gradsum, 0))
+
+
+def test_plain_c_caller_compiles_and_links():
+    """include/psmf_b200.h is valid C99 and examples/psmf_demo.c links against the library with nothing but a C
+    compiler and the CUDA runtime (no torch, no C++ types across the boundary)."""
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    cuda = "/usr/local/cuda"
+    if not gcc or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("needs gcc and the CUDA runtime headers")
+    with tempfile.TemporaryDirectory() as tmp:
+        probe = os.path.join(tmp, "probe.c")
+        with open(probe, "w") as fp:
+            fp.write('#include "psmf_b200.h"\nint main(void) { return sizeof(psmf_config) == 72 && sizeof(psmf_io) == 112 ? 0 : 1; }\n')
+        subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), probe,
+                        "-o", os.path.join(tmp, "probe")], check=True)
+        assert subprocess.run([os.path.join(tmp, "probe")]).returncode == 0
+        subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(root, "examples", "psmf_demo.c"), "-o", os.path.join(tmp, "demo"),
+                        "-L", os.path.join(root, "rpsmf_b200"), "-lpsmf_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm"],
+                       check=True)
