@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--r", type=int, default=16)
     ap.add_argument("--T", type=int, default=10_000, help="length of the resident synthetic sequence")
     ap.add_argument("--window", type=int, default=500, help="filter steps per kernel launch (= per bench step)")
+    ap.add_argument("--mask", default="iid", choices=["iid", "segments"],
+                    help="missing pattern: iid Bernoulli (default) or runs of 20 steps per row (common.py:50-76)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
@@ -51,8 +53,23 @@ def parse():
 # --------------------------------------------------------------------------------------------------
 # synthetic data (device-side, seeded): y_t = C_true x_t + sqrt(var) t_3,  x_t random walk, 20 % missing
 # --------------------------------------------------------------------------------------------------
+def segment_mask(torch, dev, T, d_loc, missing, generator, seg=20):
+    """Missing entries in runs of `seg` consecutive time steps per row, one run per row and sweep until the
+    requested ratio is reached: the pattern of the imputation experiment (common.py:50-76), time-major (T, d_loc),
+    1 = observed."""
+    M = torch.ones((T, d_loc), dtype=torch.uint8, device=dev)
+    if T <= seg + 1 or missing <= 0:
+        return M
+    rows = torch.arange(d_loc, device=dev)
+    while float(1.0 - M.float().mean()) < missing:
+        start = torch.randint(1, T - seg, (d_loc,), generator=generator, device=dev)
+        for k in range(seg):
+            M[start + k, rows] = 0
+    return M
+
+
 def make_device_data(torch, dev, d_loc, row0, d_total, r, T, dtype, seed=20261017, q=0.01, var=0.1, missing=0.2,
-                     chunk=125):
+                     chunk=125, mask="iid"):
     g = torch.Generator(device=dev)
     g.manual_seed(seed + 7919 * (row0 // max(1, d_loc) + 1))
     gx = torch.Generator(device="cpu")
@@ -63,6 +80,7 @@ def make_device_data(torch, dev, d_loc, row0, d_total, r, T, dtype, seed=2026101
     Xtrue = (x.unsqueeze(0) + torch.cumsum(steps, 0)).to(dev)
     Y = torch.empty((T, d_loc), dtype=dtype, device=dev)
     M = torch.empty((T, d_loc), dtype=torch.uint8, device=dev)
+    Mseg = segment_mask(torch, dev, T, d_loc, missing, g) if mask == "segments" else None
     for a in range(0, T, chunk):
         b = min(T, a + chunk)
         n = b - a
@@ -72,7 +90,10 @@ def make_device_data(torch, dev, d_loc, row0, d_total, r, T, dtype, seed=2026101
         chi += torch.randn((n, d_loc), generator=g, device=dev, dtype=torch.float32).square_()
         noise.div_(chi.div_(3.0).sqrt_())                  # Student-t, 3 dof (ExperimentSynthetic/data.py:47)
         del chi
-        m = torch.rand((n, d_loc), generator=g, device=dev, dtype=torch.float32) >= missing
+        if Mseg is None:
+            m = torch.rand((n, d_loc), generator=g, device=dev, dtype=torch.float32) >= missing
+        else:
+            m = Mseg[a:b] != 0
         yc = Xtrue[a:b] @ Ct.T
         yc.add_(noise.to(torch.float64), alpha=var ** 0.5)
         yc.mul_(m)                                          # zero-filled where missing (rPSMF.py:200-202)
@@ -198,7 +219,7 @@ def main():
     d_loc = row1 - row0
     T = max(args.T // W, 1) * W
     nwin = T // W
-    Y, M, C0, x0 = make_device_data(torch, dev, d_loc, row0, d, r, T, dtype)
+    Y, M, C0, x0 = make_device_data(torch, dev, d_loc, row0, d, r, T, dtype, mask=args.mask)
     init = init_state(r)
     eng = FilterEngine(d_loc, r, dtype=dtype, robust=True, device=local_rank, d_global=d, world_size=world, rank=rank,
                        ctas=args.ctas)
@@ -307,7 +328,7 @@ def main():
             scaling="strong", vs_baseline=None, dtype=args.dtype, data="synthetic",
             config=dict(workload="L: rPSMF d=%d r=%d T=%d, 20%% missing, %s; one bench step = one kernel launch over %d filter steps"
                                  % (d, r, T, args.dtype, W),
-                        d=d, r=r, T=T, window=W, missing=0.2, robust=True, rows_per_gpu=d_loc,
+                        d=d, r=r, T=T, window=W, missing=0.2, mask=args.mask, robust=True, rows_per_gpu=d_loc,
                         l2_policy="inputs larger than L2: C (%.0f MB) + Y/M windows (%.1f GB) stream from HBM every step"
                                   % (d_loc * r * esize / 1e6, W * d_loc * (esize + 1) / 1e9),
                         parallelism="rows of C sharded over %d GPU(s)" % world),

@@ -144,3 +144,25 @@ def test_plain_c_caller_compiles_and_links():
                         os.path.join(root, "examples", "psmf_demo.c"), "-o", os.path.join(tmp, "demo"),
                         "-L", os.path.join(root, "rpsmf_b200"), "-lpsmf_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm"],
                        check=True)
+
+
+def test_bench_segment_mask_generator():
+    """bench.py --mask segments: runs of 20 missing steps per row until the requested ratio (common.py:50-76)."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    g = torch.Generator(device="cpu"); g.manual_seed(1)
+    M = bench.segment_mask(torch, torch.device("cpu"), 600, 40, 0.2, g)
+    assert M.shape == (600, 40) and M.dtype == torch.uint8
+    ratio = 1.0 - M.float().mean().item()
+    assert 0.2 <= ratio < 0.26
+    assert M[0].all()                                   # segments start at t >= 1
+    for c in (0, 3, 39):                                # every maximal missing run is a union of 20-step segments
+        miss = np.concatenate([[0], (M[:, c].numpy() == 0).astype(int), [0]])
+        edges = np.flatnonzero(np.diff(miss))
+        runs = edges[1::2] - edges[0::2]
+        assert runs.size > 0 and runs.min() >= 20
+    Y, M2, C0, x0 = bench.make_device_data(torch, torch.device("cpu"), 40, 0, 40, 4, 300, torch.float64, mask="segments")
+    assert ((Y == 0) | (M2 == 1)).all() and (Y[M2 == 0] == 0).all()
