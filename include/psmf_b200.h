@@ -37,6 +37,7 @@ typedef struct psmf_engine* psmf_handle;
 
 #define PSMF_MAX_RANK 16
 #define PSMF_MAX_PEERS 8
+#define PSMF_MAILBOX_BLOB_BYTES 128   /* psmf_mailbox_export: 64-byte CUDA IPC handle + 64-byte plan record */
 
 /* storage dtype of C / Y / Yrec */
 #define PSMF_F64 0
@@ -127,7 +128,10 @@ int  psmf_get_state(psmf_handle h, void* C, double* V, double* P, double* x,
 int  psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k0, void* stream);
 
 /* synchronise the stream of the last run and report the device status word:
- * *first_bad_step = -1 if every step produced finite N/omega/phi, else the first offending step.    */
+ * *first_bad_step = -1 if every step produced finite N/omega/phi, else the first offending step.
+ * Returns PSMF_E_STATE (text in psmf_last_error) if a wait inside the kernel expired -- a peer GPU or CTA stopped
+ * answering for PSMF_SPIN_TIMEOUT_MS (environment, default 10000) -- or if a peer GPU turned out to run a
+ * different kernel; the launch has then drained with invalid results instead of hanging.              */
 int  psmf_status(psmf_handle h, int64_t* first_bad_step);
 
 /* introspection used by bench.py / tests, describing the last psmf_run: CTAs per series, threads per CTA,
@@ -142,10 +146,13 @@ int  psmf_launch_info2(psmf_handle h, int32_t* kernel, int32_t* nslot, int32_t* 
 int  psmf_set_trace(psmf_handle h, uint64_t* dev_buf, int32_t steps);
 
 /* multi-GPU row sharding (world_size > 1): NVLink mailbox for the per-step statistics exchange.
- * Each rank exports an IPC handle of its mailbox (64 bytes), gathers all ranks' handles through the
- * host-side process group, and connects.                                                            */
-int  psmf_mailbox_export(psmf_handle h, void* ipc_handle_64B);
-int  psmf_mailbox_connect(psmf_handle h, const void* all_ipc_handles, int32_t n);
+ * Each rank exports a blob of PSMF_MAILBOX_BLOB_BYTES (the CUDA IPC handle of its mailbox + a plan record: rank,
+ * shape, flags, which kernels its shard is eligible for), gathers all ranks' blobs in rank order through the
+ * host-side process group, and connects.  psmf_mailbox_connect checks that all ranks were created with the same
+ * configuration and makes the kernel choice COLLECTIVELY (every rank derives it from the same n records): the
+ * TMA-staged kernel only if every shard is eligible, else the direct-load kernel everywhere.           */
+int  psmf_mailbox_export(psmf_handle h, void* blob);
+int  psmf_mailbox_connect(psmf_handle h, const void* all_blobs, int32_t n);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,7 @@ F64, F32 = 0, 1
 ROBUST, SIMPLIFIED, CUPDATE_VT, FIXED_LAMBDA, LL_STUDENT = 1, 2, 4, 16, 32
 DYN_IDENTITY, DYN_COS, DYN_EXTERNAL = 0, 1, 3
 NSCAL = 8
+MAILBOX_BLOB_BYTES = 128
 SCAL_NAMES = ("a", "eta", "N", "omega", "phi", "sSe", "lam", "rho")
 
 # every symbol include/psmf_b200.h declares (checked by tests/test_capi_symbols.py)

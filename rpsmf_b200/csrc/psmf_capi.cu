@@ -87,6 +87,8 @@ struct psmf_engine {
     void* mbox = nullptr;
     void* peer_mbox[PSMF_MAX_PEERS] = {nullptr};
     bool connected = false;
+    int agreed_kernel = 0;             // world_size > 1: kernel all ranks agreed on in psmf_mailbox_connect (1 or 2)
+    unsigned long long spin_ns = 10ULL * 1000000000ULL;   // bounded waits of the kernels (env PSMF_SPIN_TIMEOUT_MS)
     unsigned long long step_base = 0;
     cudaStream_t last_stream = nullptr;
     std::string err;
@@ -94,7 +96,7 @@ struct psmf_engine {
 
 static std::string g_create_error;
 
-static size_t mbox_bytes() { return (size_t)2 * PSMF_MAX_PEERS * 192 * 16; }   // slots of <= nstat2_pad(16) = 176 cells
+static size_t mbox_bytes() { return (size_t)2 * PSMF_MAX_PEERS * MBOX_SLOT * 16; }   // [2 parities][peers] slots of MBOX_SLOT cells
 
 static int fail(psmf_engine* h, int code, const std::string& msg) {
     if (h)
@@ -110,7 +112,7 @@ static int fail(psmf_engine* h, int code, const std::string& msg) {
             return fail(h, PSMF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                \
     } while (0)
 
-extern "C" int psmf_version(void) { return 100; }
+extern "C" int psmf_version(void) { return 200; }
 
 extern "C" const char* psmf_last_error(psmf_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -159,6 +161,10 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
     cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     e->num_sms = sms;
+    if (const char* ev = getenv("PSMF_SPIN_TIMEOUT_MS")) {              // how long a kernel waits for a silent peer GPU / CTA
+        const long long ms = atoll(ev);
+        if (ms >= 1) e->spin_ns = (unsigned long long)ms * 1000000ULL;
+    }
 
     // ---- direct-load kernel: V1_WARPS warps per CTA, one staging tile per warp + the residual buffer ----
     int cps;
@@ -216,10 +222,12 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
             int64_t nslot = avail > 0 ? avail / (int64_t)slot : 0;
             if (nslot > nchunks_max) nslot = nchunks_max;
             if (nslot > 64) nslot = 64;
-            if (const char* ev = getenv("PSMF_NSLOT_MAX")) {            // debug knob
+#ifdef PSMF_DEBUG
+            if (const char* ev = getenv("PSMF_NSLOT_MAX")) {            // debug knob (debug builds only)
                 const int64_t cap = atoll(ev);
                 if (cap >= 2 && nslot > cap) nslot = cap;
             }
+#endif
             // a ring needs depth: with fewer than 5 slots the producer cannot keep loads, stores and the pass warps
             // apart (very large shards, where the residual buffer eats the shared memory) -> direct-load kernel
             const bool ring_ok = nchunks_max <= nslot || nslot >= 5;
@@ -366,7 +374,10 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     p.n_steps = n_steps; p.k0 = k0;
     p.n_series = h->S; p.cps = h->cps;
     p.flags = h->cfg.flags; p.dynamics = h->cfg.dynamics;
+#ifdef PSMF_DEBUG
     if (const char* ev = getenv("PSMF_DEBUG_FLAGS")) p.flags |= (int)strtol(ev, nullptr, 0) & (7 << 20);
+#endif
+    p.spin_ns = h->spin_ns;
     p.alpha = h->cfg.alpha; p.beta = h->cfg.beta;
     p.world = h->cfg.world_size; p.rank = h->cfg.rank;
     if (p.world > 1) {
@@ -391,6 +402,14 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
                 (h->cfg.kernel == 2 || (h->cfg.kernel == 0 && h->ntiles >= 2 * (V2_CWARPS + 1)));
     if (h->cfg.kernel == 2 && !use2)
         return fail(h, PSMF_E_INVALID, "kernel=2 requested but Y/M are not 16-byte aligned (or dynamics is external)");
+    if (p.world > 1) {
+        // row sharding: the kernel is a collective decision (psmf_mailbox_connect) -- the two kernels exchange
+        // different statistics vectors, so a rank must never pick one from local facts alone
+        if (h->agreed_kernel == 2 && !aligned)
+            return fail(h, PSMF_E_INVALID, "the ranks agreed on the TMA-staged kernel but this rank's Y/M are not 16-byte aligned "
+                                           "(pad ldy/ldm to a multiple of 16 bytes, or create every engine with kernel=1)");
+        use2 = h->agreed_kernel == 2;
+    }
     if (use2) {
         p.cps = h->cps2;
         p.nslot = h->nslot;
@@ -399,7 +418,9 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
         // with the ring and leave issue slots to the producer -- measured optimum at r = 16 under the power cap;
         // resident in shared memory: every warp helps
         p.npw = h->resident2 ? V2_CWARPS : 12;
+#ifdef PSMF_DEBUG
         if (const char* ev = getenv("PSMF_NPW")) { const int v = atoi(ev); if (v >= 1 && v <= V2_CWARPS) p.npw = v; }
+#endif
         p.gparams = h->gparams;
         CK(h, LAUNCH_S[h->R](p, h->cfg.dtype, h->cps2 + 1, h->dyn_smem2, st, true));
         h->last_kernel = 2;
@@ -419,6 +440,21 @@ extern "C" int psmf_status(psmf_handle h, int64_t* first_bad_step) {
     CK(h, cudaStreamSynchronize(h->last_stream));
     long long v = -1;
     CK(h, cudaMemcpy(&v, h->status, sizeof(v), cudaMemcpyDeviceToHost));
+    if (v >= 0 && (v & (STATUS_TIMEOUT | STATUS_MISMATCH)) != 0) {
+        const long long step = v & 0xFFFFFFFFFFFFLL;
+        if (first_bad_step) *first_bad_step = (int64_t)step;
+        if (v & STATUS_TIMEOUT) {
+            static const char* const SITE[] = {"?", "tagged cell", "NVLink mailbox (peer GPU)", "mbarrier", "grid barrier",
+                                               "chunk ring", "CTA partials"};
+            const int where = (int)((v >> 48) & 0xFF);
+            char buf[256];
+            snprintf(buf, sizeof(buf), "a kernel wait made no progress for %.1f s at step %lld (%s): a peer GPU or CTA is gone; "
+                     "the results of this launch are invalid", (double)h->spin_ns * 1e-9, step, SITE[where < 7 ? where : 0]);
+            return fail(h, PSMF_E_STATE, buf);
+        }
+        return fail(h, PSMF_E_STATE, "a peer GPU runs a different kernel / statistics layout (mailbox header mismatch at step " +
+                                         std::to_string(step) + ")");
+    }
     if (first_bad_step) *first_bad_step = (int64_t)v;
     return PSMF_OK;
 }
@@ -448,29 +484,73 @@ extern "C" int psmf_set_trace(psmf_handle h, uint64_t* dev_buf, int32_t steps) {
     return PSMF_OK;
 }
 
-extern "C" int psmf_mailbox_export(psmf_handle h, void* ipc_handle_64B) {
-    if (!h || !ipc_handle_64B) return PSMF_E_INVALID;
+// Plan record that travels with the IPC handle (bytes 64..127 of the blob): every rank sees every record and
+// derives the same decision from them, so the ranks can never run different kernels against each other.
+struct plan_record {
+    int32_t version, r, dtype, flags, dynamics, world, kernel_pref, eligible2, auto2, rank;
+    int64_t d_global;
+    int32_t pad[4];
+};
+static_assert(sizeof(plan_record) <= 64, "plan record must fit the second half of the blob");
+
+static plan_record make_plan(const psmf_engine* h) {
+    plan_record r;
+    memset(&r, 0, sizeof(r));
+    r.version = psmf_version();
+    r.r = h->R; r.dtype = h->cfg.dtype; r.flags = h->cfg.flags; r.dynamics = h->cfg.dynamics; r.world = h->cfg.world_size;
+    r.kernel_pref = h->cfg.kernel; r.rank = h->cfg.rank; r.d_global = h->cfg.d_global;
+    r.eligible2 = (h->cps2 > 0 && h->cfg.dynamics != PSMF_DYN_EXTERNAL) ? 1 : 0;
+    r.auto2 = (r.eligible2 && h->ntiles >= 2 * (V2_CWARPS + 1)) ? 1 : 0;
+    return r;
+}
+
+extern "C" int psmf_mailbox_export(psmf_handle h, void* blob_128B) {
+    if (!h || !blob_128B) return PSMF_E_INVALID;
     if (h->cfg.world_size < 2 || !h->mbox) return fail(h, PSMF_E_STATE, "engine was created with world_size == 1");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CK(h, cudaSetDevice(h->cfg.device));
     cudaIpcMemHandle_t hd;
     CK(h, cudaIpcGetMemHandle(&hd, h->mbox));
-    memcpy(ipc_handle_64B, &hd, sizeof(hd));
+    memset(blob_128B, 0, PSMF_MAILBOX_BLOB_BYTES);
+    memcpy(blob_128B, &hd, sizeof(hd));
+    const plan_record pr = make_plan(h);
+    memcpy((char*)blob_128B + 64, &pr, sizeof(pr));
     return PSMF_OK;
 }
 
-extern "C" int psmf_mailbox_connect(psmf_handle h, const void* all_ipc_handles, int32_t n) {
-    if (!h || !all_ipc_handles) return PSMF_E_INVALID;
-    if (n != h->cfg.world_size || n < 2) return fail(h, PSMF_E_INVALID, "need one IPC handle per rank");
+extern "C" int psmf_mailbox_connect(psmf_handle h, const void* all_blobs, int32_t n) {
+    if (!h || !all_blobs) return PSMF_E_INVALID;
+    if (n != h->cfg.world_size || n < 2) return fail(h, PSMF_E_INVALID, "need one blob per rank");
     CK(h, cudaSetDevice(h->cfg.device));
-    const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)all_ipc_handles;
+    const char* blobs = (const char*)all_blobs;
+    // ---- collective plan: same inputs on every rank -> same decision on every rank ----
+    const plan_record mine = make_plan(h);
+    bool any_forced1 = false, any_forced2 = false, all_eligible2 = true, all_auto2 = true;
+    for (int i = 0; i < n; ++i) {
+        plan_record pr;
+        memcpy(&pr, blobs + (size_t)i * PSMF_MAILBOX_BLOB_BYTES + 64, sizeof(pr));
+        if (pr.version != mine.version || pr.r != mine.r || pr.dtype != mine.dtype || pr.flags != mine.flags ||
+            pr.dynamics != mine.dynamics || pr.world != mine.world || pr.d_global != mine.d_global || pr.rank != i)
+            return fail(h, PSMF_E_INVALID, "rank " + std::to_string(i) + " was created with a different configuration "
+                                           "(version / r / dtype / flags / dynamics / world_size / d_global / rank order)");
+        any_forced1 = any_forced1 || pr.kernel_pref == 1;
+        any_forced2 = any_forced2 || pr.kernel_pref == 2;
+        all_eligible2 = all_eligible2 && pr.eligible2 != 0;
+        all_auto2 = all_auto2 && (pr.auto2 != 0 || (pr.kernel_pref == 2 && pr.eligible2 != 0));
+    }
+    if (any_forced1 && any_forced2) return fail(h, PSMF_E_INVALID, "ranks disagree: kernel=1 and kernel=2 were both forced");
+    if (any_forced2 && !all_eligible2)
+        return fail(h, PSMF_E_INVALID, "kernel=2 was forced but not every rank's shard is eligible for the TMA-staged kernel");
+    h->agreed_kernel = any_forced2 ? 2 : (any_forced1 ? 1 : (all_auto2 ? 2 : 1));
     for (int i = 0; i < n; ++i) {
         if (i == h->cfg.rank) {
             h->peer_mbox[i] = h->mbox;
             continue;
         }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, blobs + (size_t)i * PSMF_MAILBOX_BLOB_BYTES, sizeof(hd));
         void* ptr = nullptr;
-        CK(h, cudaIpcOpenMemHandle(&ptr, hs[i], cudaIpcMemLazyEnablePeerAccess));
+        CK(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
         h->peer_mbox[i] = ptr;
     }
     h->connected = true;

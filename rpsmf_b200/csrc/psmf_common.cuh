@@ -22,8 +22,11 @@ constexpr int MAX_PEERS = 8;
 // flags (mirror include/psmf_b200.h)
 constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16, F_LL_STUDENT = 32;
 constexpr int DYN_IDENTITY = 0, DYN_COS = 1, DYN_EXTERNAL = 3;
-// debug-only flag bits (env PSMF_DEBUG_FLAGS, never set by the Python surface): results are WRONG with them
-constexpr int F_DBG_NOCOMPUTE = 1 << 20, F_DBG_NOSTORE = 1 << 21, F_DBG_NOYM = 1 << 22;
+// debug-only flag bits (env PSMF_DEBUG_FLAGS; results are WRONG with them): compiled in only with -DPSMF_DEBUG,
+// release builds of the library carry neither the flags nor the environment knobs
+#ifdef PSMF_DEBUG
+constexpr int F_DBG_NOCOMPUTE = 1 << 20, F_DBG_NOSTORE = 1 << 21;
+#endif
 
 // ---- tile layout and statistics vector ------------------------------------------------------------
 // Inside a 32-row tile, element (row i, column j) lives at  j*32 + (i ^ ((j & 7) << 2)).
@@ -90,7 +93,23 @@ struct KParams {
     double* gparams;          // pipelined kernel: [2][2 * MAXR] parameter sets published by the control CTA
     int32_t trace_steps;      // debug: number of steps recorded in `trace`
     unsigned long long* trace; // debug: [trace_steps][8] globaltimer stamps of CTA 0 (or nullptr)
+    unsigned long long spin_ns; // a wait (tagged cell, mbarrier, grid barrier, NVLink mailbox) that makes no progress for
+                                // this long gives up: status word <- STATUS_TIMEOUT | step, abort word (bar[7]) <- 1
 };
+
+// ---- tags and the status word --------------------------------------------------------------------
+// Tags of the 16-byte cells: never 0 (zeroed memory must not look valid), period 2^31 steps.  A stale cell holds
+// the tag of two steps earlier (two parities), so a wrapped tag can never be mistaken for a current one.
+__host__ __device__ constexpr uint32_t tag_of(unsigned long long step) { return (uint32_t)step | 0x80000000u; }
+// status word (KParams.status, int64): -1 = ok, >= 0 = first step with a non-finite N / omega / phi / x,
+// STATUS_TIMEOUT | (where << 48) | step = a bounded wait expired (peer GPU or CTA gone): psmf_status -> PSMF_E_STATE
+constexpr long long STATUS_TIMEOUT = 1LL << 62;
+constexpr long long STATUS_MISMATCH = 1LL << 61;     // peer runs another kernel / statistics layout (mailbox header)
+constexpr int ABORT_WORD = 7;                          // index into KParams.bar
+enum SpinSite { SPIN_CELL = 1, SPIN_PEER = 2, SPIN_MBAR = 3, SPIN_GRID = 4, SPIN_RING = 5, SPIN_PARTIALS = 6 };
+// NVLink mailbox: [2 parities][MAX_PEERS] slots of MBOX_SLOT tagged cells; the last cell of a slot is the header
+// {kernel id, statistics count} that every receiver checks, so the stride is the same whatever kernel a peer runs
+constexpr int MBOX_SLOT = 192;
 
 struct LaunchShape {
     int threads;

@@ -82,22 +82,63 @@ __device__ __forceinline__ void cell_store(uint4* cell, double v, uint32_t tag) 
     const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
-__device__ __forceinline__ double cell_poll(const uint4* cell, uint32_t tag) {
+// ---- bounded waits ------------------------------------------------------------------------------------
+// Every wait of the kernels (tagged cells, NVLink mailbox, mbarriers, grid barrier, chunk ring) goes through a
+// Spin guard: the fast path is a counter, every 64th failed attempt looks at the abort word and the clock.  A wait
+// without progress for KParams.spin_ns marks the status word (STATUS_TIMEOUT | site | step) and raises the abort
+// word; every other wait of the grid then gives up as well, the launch drains (results are garbage) and
+// psmf_status reports PSMF_E_STATE -- a dead peer GPU or CTA cannot hang the survivors.
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+// slow path (every 64th failed attempt); takes scalars, not KParams, so that the kernel parameters stay in the
+// constant bank.  Returns the start time of the wait, or ~0 when the wait has expired / the grid is aborting.
+static __device__ __noinline__ unsigned long long spin_slow(unsigned long long* bar, long long* status, unsigned long long spin_ns,
+                                                            unsigned long long t0, int where, long long step) {
+    if (*reinterpret_cast<volatile unsigned long long*>(bar + ABORT_WORD) != 0ULL) return ~0ULL;
+    const unsigned long long now = gtimer();
+    if (t0 == 0ULL) return now;
+    if (now - t0 < spin_ns) return t0;
+    const unsigned long long code = (unsigned long long)STATUS_TIMEOUT | ((unsigned long long)where << 48) |
+                                    ((unsigned long long)step & 0xFFFFFFFFFFFFULL);
+    atomicCAS((unsigned long long*)status, ~0ULL, code);
+    atomicExch(bar + ABORT_WORD, 1ULL);
+    return ~0ULL;
+}
+struct Spin {
+    unsigned n = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ bool expired(const KParams& p, int where, long long step) {
+        if ((++n & 63u) != 0u) return false;
+        t0 = spin_slow(p.bar, p.status, p.spin_ns, t0, where, step);
+        return t0 == ~0ULL;
+    }
+};
+
+__device__ __forceinline__ double cell_poll(const KParams& p, const uint4* cell, uint32_t tag, long long step) {
     uint32_t lo, t0, hi, t1;
-    do {
+    Spin sp;
+    for (;;) {
         asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(cell) : "memory");
-    } while (t0 != tag || t1 != tag);
+        if (t0 == tag && t1 == tag) break;
+        if (sp.expired(p, SPIN_CELL, step)) break;
+    }
     return __hiloint2double((int)hi, (int)lo);
 }
 __device__ __forceinline__ void cell_store_sys(uint4* cell, double v, uint32_t tag) {      // peer GPU over NVLink
     const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
     asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
-__device__ __forceinline__ double cell_poll_sys(const uint4* cell, uint32_t tag) {
+__device__ __forceinline__ double cell_poll_sys(const KParams& p, const uint4* cell, uint32_t tag, long long step) {
     uint32_t lo, t0, hi, t1;
-    do {
+    Spin sp;
+    for (;;) {
         asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(cell) : "memory");
-    } while (t0 != tag || t1 != tag);
+        if (t0 == tag && t1 == tag) break;
+        if (sp.expired(p, SPIN_PEER, step)) break;
+    }
     return __hiloint2double((int)hi, (int)lo);
 }
 
@@ -108,11 +149,13 @@ __device__ __forceinline__ void sync_n(int n) { asm volatile("bar.sync %0, %1;" 
 
 // All CTAs of the grid are co-resident (cooperative launch).  `target` grows monotonically.
 template <int BAR = 0>
-__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target, int nthr, int tid) {
+__device__ __forceinline__ void grid_barrier(const KParams& p, unsigned long long target, int nthr, int tid, long long step) {
     sync_n<BAR>(nthr);
     if (tid == 0) {
-        red_release_gpu(bar, 1ULL);
-        while (ld_acquire_gpu(bar) < target) {
+        red_release_gpu(p.bar, 1ULL);
+        Spin sp;
+        while (ld_acquire_gpu(p.bar) < target) {
+            if (sp.expired(p, SPIN_GRID, step)) break;
         }
     }
     sync_n<BAR>(nthr);
@@ -456,7 +499,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         if (lane < R) {
             sh.x[lane] = xn;
             if (writer && p.X_out != nullptr) p.X_out[((int64_t)series * p.n_steps + t) * R + lane] = xn;
-            if (p.grad_out != nullptr && p.dynamics == DYN_COS) {
+            if (p.grad_out != nullptr && (p.dynamics == DYN_COS || p.dynamics == DYN_EXTERNAL)) {
                 // d ell_k / d theta = J_theta' d ell_k / d f with f = x_bar, s = f'Vf + eta = N, e = y - M C f
                 // (psmf.py:57-64,167-177; rpsmf.py:62-71,196-200); C'Me = b (rho + a), n = n_obs, q = q1
                 const double vsf = 0.5 * (sh.vx[lane] + sh.vxt[lane]);
@@ -469,7 +512,9 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
                     gf = (nobs / N - q1 / (N * N)) * vsf - cte / N;
                 }
                 const double kabs = (double)(p.k0 + t);
-                sh.grad[lane] += gf * (6.283185307179586 * kabs * sh.fd[lane]);   // J_theta = diag(-2 pi k sin(.))
+                // cos dynamics: J_theta = diag(-2 pi k sin(.)); external dynamics: the caller owns f and applies its own
+                // J_theta' to d ell / d f (one step per launch)
+                sh.grad[lane] += p.dynamics == DYN_COS ? gf * (6.283185307179586 * kabs * sh.fd[lane]) : gf;
             }
         }
         if (lane == 0) {
@@ -520,22 +565,33 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
 // can only be one step ahead of its slowest peer (it needs that peer's cells of the current step to proceed).
 template <int NST, int NSP, int BAR = 0>
 __device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restrict__ tot, double* __restrict__ /*tmp*/, int tid,
-                                             int64_t t, int part, int nthr) {
+                                             int64_t t, int part, int nthr, int kernel_id) {
     const unsigned long long step = p.step_base + (unsigned long long)t;
     const int parity = (int)(step & 1ULL);
-    const uint32_t tag = (uint32_t)(step + 1ULL);
+    const uint32_t tag = tag_of(step + 1ULL);
+    const double header = (double)(kernel_id * 4096 + NST);          // what this GPU sends: kernel and statistics layout
     if (part == 0) {
-        for (int e = tid; e < NST; e += nthr) {
-            const double v = tot[e];
+        for (int e = tid; e <= NST; e += nthr) {
+            const double v = e < NST ? tot[e] : header;
+            const int cell = e < NST ? e : MBOX_SLOT - 1;
             for (int pr = 0; pr < p.world; ++pr)
                 if (pr != p.rank)
-                    cell_store_sys(reinterpret_cast<uint4*>(p.mbox_peer[pr]) + ((size_t)parity * MAX_PEERS + p.rank) * NSP + e, v, tag);
+                    cell_store_sys(reinterpret_cast<uint4*>(p.mbox_peer[pr]) + ((size_t)parity * MAX_PEERS + p.rank) * MBOX_SLOT + cell, v, tag);
         }
     }
-    const uint4* local = reinterpret_cast<const uint4*>(p.mbox_local) + (size_t)parity * MAX_PEERS * NSP;
+    const uint4* local = reinterpret_cast<const uint4*>(p.mbox_local) + (size_t)parity * MAX_PEERS * MBOX_SLOT;
+    if (tid == nthr - 1) {
+        // all ranks must run the same kernel with the same statistics vector (the host agrees on it in
+        // psmf_mailbox_connect); a mismatch would add unrelated numbers: flag it instead
+        for (int src = 0; src < p.world; ++src)
+            if (src != p.rank && cell_poll_sys(p, local + (size_t)src * MBOX_SLOT + MBOX_SLOT - 1, tag, t) != header) {
+                if (*reinterpret_cast<volatile unsigned long long*>(p.bar + ABORT_WORD) == 0ULL)
+                    atomicCAS((unsigned long long*)p.status, ~0ULL, (unsigned long long)STATUS_MISMATCH | (unsigned long long)t);
+            }
+    }
     for (int e = tid; e < NST; e += nthr) {
         double s = 0.0;
-        for (int src = 0; src < p.world; ++src) s += (src == p.rank) ? tot[e] : cell_poll_sys(local + (size_t)src * NSP + e, tag);
+        for (int src = 0; src < p.world; ++src) s += (src == p.rank) ? tot[e] : cell_poll_sys(p, local + (size_t)src * MBOX_SLOT + e, tag, t);
         tot[e] = s;                                              // entry e is read and written by this thread only
     }
     sync_n<BAR>(nthr);
@@ -552,7 +608,7 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
     if (p.cps == 1) {
         for (int e = tid; e < NST; e += nthr) tot[e] = part_v[e];
         sync_n<BAR>(nthr);
-        if (p.world > 1) gpu_exchange<NST, NSP, BAR>(p, tot, part_v, tid, t, part, nthr);
+        if (p.world > 1) gpu_exchange<NST, NSP, BAR>(p, tot, part_v, tid, t, part, nthr, 1);
         return;
     }
     const int parity = (int)(t & 1);
@@ -561,7 +617,7 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
         double* mine = p.partials + ((size_t)parity * cps + part) * NSP;
         for (int e = tid; e < NST; e += nthr) mine[e] = part_v[e];
         stamp(p, t, 3);
-        grid_barrier<BAR>(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), nthr, tid);
+        grid_barrier<BAR>(p, (unsigned long long)gridDim.x * (unsigned long long)(t + 1), nthr, tid, t);
         stamp(p, t, 4);
         const double* basep = p.partials + (size_t)parity * cps * NSP;
         for (int e = tid; e < NST; e += nthr) {
@@ -577,7 +633,7 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
         double* totals = pT + (size_t)NSP * pstr;
         for (int e = tid; e < NST; e += nthr) pT[(size_t)e * pstr + part] = part_v[e];
         stamp(p, t, 3);
-        grid_barrier<BAR>(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 1), nthr, tid);
+        grid_barrier<BAR>(p, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 1), nthr, tid, t);
         const int nw = nthr >> 5;
         for (int e = part + warp * cps; e < NST; e += nw * cps) {
             const double* src = pT + (size_t)e * pstr;
@@ -594,12 +650,12 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
             s = warp_allsum(s);
             if (lane == 0) totals[e] = s;
         }
-        grid_barrier<BAR>(p.bar, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 2), nthr, tid);
+        grid_barrier<BAR>(p, (unsigned long long)gridDim.x * (unsigned long long)(2 * t + 2), nthr, tid, t);
         stamp(p, t, 4);
         for (int e = tid; e < NST; e += nthr) tot[e] = __ldcg(totals + e);
     }
     sync_n<BAR>(nthr);
-    if (p.world > 1) gpu_exchange<NST, NSP, BAR>(p, tot, part_v, tid, t, part, nthr);
+    if (p.world > 1) gpu_exchange<NST, NSP, BAR>(p, tot, part_v, tid, t, part, nthr, 1);
 }
 
 // ---- direct-load persistent kernel: C tiles are read from / written to global memory by the warp that

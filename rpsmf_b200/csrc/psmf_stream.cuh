@@ -87,8 +87,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(const KParams& p, uint64_t* bar, uint32_t parity, long long step) {
+    Spin sp;
     while (!mbar_try_wait(bar, parity)) {
+        if (sp.expired(p, SPIN_MBAR, step)) break;
     }
 }
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -202,16 +204,19 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
         // requested for the slot; once that is ours, the previous phase is complete and the parity is unambiguous.
         if (streaming) {
             const int lap = (int)(kk / nslot);
+            Spin sp;
             while (ps.gen[slot] < lap) {
+                if (sp.expired(p, SPIN_RING, pass)) break;
             }
         }
-        mbar_wait(&ps.full[slot], parity);
+        mbar_wait(p, &ps.full[slot], parity, pass);
         wait_full += clock64() - c0;
         const int64_t row = (int64_t)(tb + tl) * TILE + lane;
         const int rl = tl * TILE + lane;
         const bool inb = row < p.d;
         T* tile = reinterpret_cast<T*>(sb) + (size_t)i * (R * TILE);
 
+#ifdef PSMF_DEBUG
         if ((p.flags & F_DBG_NOCOMPUTE) != 0) {
             fence_proxy_async();
             __syncwarp();
@@ -221,6 +226,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
             }
             continue;
         }
+#endif
         // ---- phase 1, lane = row ----
         double c[R];
 #pragma unroll
@@ -303,7 +309,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
         if (pass + 1 <= p.n_steps)
             nx = load_ym<T>(p, Yb, Mb, pass + 1, (int64_t)(tb + wp) * TILE + lane, true, pass + 1 < p.n_steps);
         // per-warp sums -> ps.red; the reduce warp adds them and takes it from there, this warp moves on
-        if (pass >= 1) mbar_wait(&ps.red_free, (uint32_t)((pass - 1) & 1));
+        if (pass >= 1) mbar_wait(p, &ps.red_free, (uint32_t)((pass - 1) & 1), pass);
         double* r0 = ps.red + wp * NSP2;
         const int kq = lane & 3, mm = lane >> 2;
 #pragma unroll
@@ -378,9 +384,11 @@ __device__ void s_producer(const KParams& p, DataSmem<R>& ps, unsigned char* slo
         int sk = 0, slot = 0;                         // chunk-in-pass index / slot of the next store
         uint32_t par = 0;
         for (int64_t j = 0; j < total; ++j) {
-            mbar_wait(&ps.done[slot], par);                                       // chunk j processed
+            mbar_wait(p, &ps.done[slot], par, j);                                     // chunk j processed
             unsigned char* sb = slots + (size_t)slot * L::SLOT;
+#ifdef PSMF_DEBUG
             if ((p.flags & F_DBG_NOSTORE) == 0)
+#endif
                 bulk_store(Cb + (size_t)sk * CHUNK_ELEMS, sb, sk == nchunks - 1 ? last_bytes : full_bytes);
             bulk_commit();
             if (lc < total) {
@@ -407,11 +415,11 @@ __device__ void s_producer(const KParams& p, DataSmem<R>& ps, unsigned char* slo
         }
         for (int64_t pass = 1; pass < npass; ++pass)
             for (int k = 0; k < nchunks; ++k) {
-                mbar_wait(&ps.done[k], (uint32_t)((pass - 1) & 1));               // pass warps are done with pass-1
+                mbar_wait(p, &ps.done[k], (uint32_t)((pass - 1) & 1), pass);               // pass warps are done with pass-1
                 mbar_arrive(&ps.full[k]);                                          // C stays resident
             }
         for (int k = 0; k < nchunks; ++k) {
-            mbar_wait(&ps.done[k], (uint32_t)((npass - 1) & 1));
+            mbar_wait(p, &ps.done[k], (uint32_t)((npass - 1) & 1), npass);
             bulk_store(Cb + (size_t)k * CHUNK_ELEMS, slots + (size_t)k * L::SLOT, k == nchunks - 1 ? last_bytes : full_bytes);
             bulk_commit();
         }
@@ -459,10 +467,10 @@ __device__ void reduce_warp(const KParams& p, DataSmem<R>& ps, int lane, int NPW
     for (int64_t t = 0; t < p.n_steps; ++t) {
         const int b = (int)(t & 1);
         // the partial cells outlive the launch: their tags count the steps of the engine, not of the launch
-        const uint32_t ptag = (uint32_t)(p.step_base + (unsigned long long)t + 1ULL);
+        const uint32_t ptag = tag_of(p.step_base + (unsigned long long)t + 1ULL);
         uint4* base = pcells + (size_t)b * NSP2 * pstr;
         // (1) CTA partial of pass t: per-warp sums in fixed warp order -> tagged cells [parity][entry][cta]
-        mbar_wait(&ps.red_full, (uint32_t)b);
+        mbar_wait(p, &ps.red_full, (uint32_t)b, t);
         {
             double sum[NE];
 #pragma unroll
@@ -485,6 +493,7 @@ __device__ void reduce_warp(const KParams& p, DataSmem<R>& ps, int lane, int NPW
             const uint4* row = base + (size_t)e * pstr;
             double v[8];
             bool ok;
+            Spin sp;
             do {
                 ok = true;
 #pragma unroll
@@ -496,9 +505,10 @@ __device__ void reduce_warp(const KParams& p, DataSmem<R>& ps, int lane, int NPW
                     ok = ok && (c >= ndata || (t0 == ptag && t1 == ptag));
                     v[j] = (c < ndata) ? __hiloint2double((int)hi, (int)lo) : 0.0;
                 }
+                if (!ok && sp.expired(p, SPIN_PARTIALS, t)) ok = true;
             } while (!__all_sync(FULL, ok));
             const double sum = warp_allsum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])));
-            if (lane == 0) cell_store(totals + (size_t)b * NSP2 + e, sum, (uint32_t)(t + 1));
+            if (lane == 0) cell_store(totals + (size_t)b * NSP2 + e, sum, tag_of((unsigned long long)t + 1ULL));
             __syncwarp();
         }
     }
@@ -516,10 +526,10 @@ __device__ void control_reduce(const KParams& p, ControlSmem<R>& cs) {
         double* tot2 = cs.tot2[b];
         if (t >= 2) named_bar_sync(CB_EMPTY + b, (int)blockDim.x);   // the solvers are done with the sums of step t-2
         stamp(p, t, 2, C_SOLVERS);
-        for (int e = tid; e < NST2; e += NTHR) tot2[e] = cell_poll(totals + (size_t)b * NSP2 + e, (uint32_t)(t + 1));
+        for (int e = tid; e < NST2; e += NTHR) tot2[e] = cell_poll(p, totals + (size_t)b * NSP2 + e, tag_of((unsigned long long)t + 1ULL), t);
         sync_n<CB_R>(NTHR);
         stamp(p, t, 4, C_SOLVERS);
-        if (p.world > 1) gpu_exchange<NST2, NSP2, CB_R>(p, tot2, cs.tmp2, tid, t, 0, NTHR);
+        if (p.world > 1) gpu_exchange<NST2, NSP2, CB_R>(p, tot2, cs.tmp2, tid, t, 0, NTHR, 2);
         stamp(p, t, 13, C_SOLVERS);
         __threadfence_block();
         named_bar_arrive(CB_FULL + b, (int)blockDim.x);
@@ -564,8 +574,8 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
     sync_n<CB_S>(NTHR);
     predict_cta<R, CB_S>(p, sh, tid, p.k0, 0, NTHR);               // xbar_0, Pbar_0, a_0, w1/w0
     if (tid < R) {                                                 // set 0 = {0, xbar_0}
-        cell_store(cells + tid, 0.0, 1u);
-        cell_store(cells + R + tid, sh.xb[tid], 1u);
+        cell_store(cells + tid, 0.0, tag_of(1ULL));
+        cell_store(cells + R + tid, sh.xb[tid], tag_of(1ULL));
     }
 
     for (int64_t t = 0; t < n; ++t) {
@@ -637,11 +647,13 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
             const double xh = warp_allsum(xj * hj);
             const double xax = warp_allsum(xj * ax);
             const double w1 = sh.w1, w0 = sh.w0;
-            const double q1 = a2[NGm + R + 0] - 2.0 * xh + xax;
+            // q1 is rebuilt from raw second moments: when the residual is far below the signal the three terms cancel
+            // and the rounding error (eps * gamma) can leave q1 slightly negative -> clamp
+            const double q1 = fmax(a2[NGm + R + 0] - 2.0 * xh + xax, 0.0);
             const double q0 = a2[NGm + R + 1];
             if (lane < R) sh.tot[NGm + lane] = w1 * (hj - ax);                 // b = w1 sum m e c
             if (lane == 0) {
-                sh.tot[NGm + R + 0] = w1 * q1 + w0 * q0;                       // s = diff' Ri diff
+                sh.tot[NGm + R + 0] = w1 * q1 + (q0 != 0.0 ? w0 * q0 : 0.0);  // s = diff' Ri diff (a = 0: w0 = inf only matters with missing rows)
                 sh.tot[NGm + R + 1] = q1;
                 sh.tot[NGm + R + 2] = q0;
                 sh.tot[NGm + R + 3] = a2[NGm + R + 2];
@@ -705,8 +717,8 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
                 } else {
                     xnext = xn;                        // external dynamics run one step per launch: set n is never used
                 }
-                cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + lane, sh.g[lane], (uint32_t)(t + 2));
-                cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + R + lane, xnext, (uint32_t)(t + 2));
+                cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + lane, sh.g[lane], tag_of((unsigned long long)t + 2ULL));
+                cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + R + lane, xnext, tag_of((unsigned long long)t + 2ULL));
                 cs.kb[lane] = kbj;
             }
             stamp(p, t, 6);
@@ -788,12 +800,12 @@ template <int R>
 __device__ __forceinline__ void fetch_params(const KParams& p, DataSmem<R>& ps, int64_t set, int wp, int lane) {
     if (wp == 0) {
         const uint4* cells = reinterpret_cast<const uint4*>(p.gparams) + (size_t)(set & 1) * 2 * R;
-        for (int i = lane; i < 2 * R; i += 32) ps.par[set & 1][i] = cell_poll(cells + i, (uint32_t)(set + 1));
+        for (int i = lane; i < 2 * R; i += 32) ps.par[set & 1][i] = cell_poll(p, cells + i, tag_of((unsigned long long)set + 1ULL), set);
         __threadfence_block();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ps.par_full[set & 1]);
     }
-    mbar_wait(&ps.par_full[set & 1], (uint32_t)((set >> 1) & 1));
+    mbar_wait(p, &ps.par_full[set & 1], (uint32_t)((set >> 1) & 1), set);
 }
 
 template <int R, typename T>

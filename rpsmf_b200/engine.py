@@ -187,7 +187,9 @@ class FilterEngine:
             raise ValueError("run_host supports single-series engines")
         T, d = Y_host.shape[0], self.d
         dev = self.device
-        if not hasattr(self, "_hb") or self._hb[0].shape[0] < window or self._hb[0].shape[1] != Y_host.shape[1]:
+        key = (int(window), int(Y_host.shape[1]), M_host is not None)
+        if getattr(self, "_hb_key", None) != key:
+            self._hb_key = key
             ld = Y_host.shape[1]
             self._hb = [torch.empty((window, ld), dtype=self.dtype, device=dev) for _ in range(2)]
             self._hm = [torch.empty((window, ld), dtype=torch.uint8, device=dev) for _ in range(2)] if M_host is not None else None
@@ -196,6 +198,7 @@ class FilterEngine:
         Xh = torch.empty((T, self.r), dtype=torch.float64).pin_memory() if want_X else None
         main = torch.cuda.current_stream(dev)
         cs = self._copy_stream
+        cs.wait_stream(main)                        # staging buffers may still be read by an earlier run_host call
         nwin = (T + window - 1) // window
         copied = [None, None]
         done = [None, None]
@@ -227,13 +230,16 @@ class FilterEngine:
             ev = torch.cuda.Event()
             ev.record(main)
             done[slot] = ev
+        if want_X:
+            done[(nwin - 1) & 1].synchronize()      # the returned host tensor is complete when the caller reads it
         return Xh
 
     def connect(self, dist):
-        """Row sharding over several GPUs: exchange the CUDA IPC handles of the NVLink mailboxes through the
-        process group `dist` (torch.distributed, any backend) and map every peer's mailbox."""
+        """Row sharding over several GPUs: exchange the mailbox blobs (CUDA IPC handle + plan record) through the
+        process group `dist` (torch.distributed, any backend) and map every peer's mailbox.  The library derives
+        the kernel choice from ALL ranks' records, so every rank runs the same kernel."""
         world = dist.get_world_size()
-        buf = (C.c_ubyte * 64)()
+        buf = (C.c_ubyte * _capi.MAILBOX_BLOB_BYTES)()
         self._ck(self._L.psmf_mailbox_export(self._h, buf))
         mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
         backend = dist.get_backend()

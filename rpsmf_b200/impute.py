@@ -85,6 +85,8 @@ def _fit(Y, C, X, d, n, r, M, Mmiss, V, Q0, R0, P, lambda0, sig, Iter, YorigInt,
             if bad >= 0:
                 Epred[:, i + 1] = np.nan; Efull[:, i + 1] = np.nan
             RunTime[:, i + 1] = time.time() - t0
+        if out is None:                                                         # Iter = 0: nothing was filtered
+            return (Epred, Efull, RunTime, 0.0, {}) if return_details else (Epred, Efull, RunTime, 0.0)   # bounds are all zero
         sc = out["scal"]
         if robust:
             U = sc[:, _capi.SCAL_NAMES.index("a")].unsqueeze(1) * Mt.to(f64) + sc[:, _capi.SCAL_NAMES.index("eta")].unsqueeze(1)

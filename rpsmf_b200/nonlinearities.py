@@ -98,3 +98,37 @@ def jacobian_x(nonlinearity, theta, x, t):
     except Exception:
         pass
     return Fd
+
+
+def jacobian_theta(nonlinearity, theta, x, t):
+    """J = d f / d theta at (theta, x, t) as an (r, p) matrix, p = theta.size (the reference differentiates the
+    incremental likelihood with autograd, psmf.py:41,167-177; here d ell / d f comes from the kernel and the chain
+    rule is closed with this Jacobian).  Complex-step when the callable is analytic, else central differences."""
+    theta = np.asarray(theta, dtype=np.float64)
+    shape = theta.shape
+    th = theta.reshape(-1)
+    p = th.size
+    r = np.asarray(x).reshape(-1).size
+    Jd = np.zeros((r, p))
+    for j in range(p):
+        h = 1e-6 * max(1.0, abs(float(th[j])))
+        tp, tm = th.copy(), th.copy()
+        tp[j] += h
+        tm[j] -= h
+        Jd[:, j] = (np.asarray(nonlinearity(tp.reshape(shape), x, t), dtype=np.float64).reshape(r)
+                    - np.asarray(nonlinearity(tm.reshape(shape), x, t), dtype=np.float64).reshape(r)) / (2 * h)
+    try:
+        Jc = np.zeros((r, p))
+        h = 1e-30
+        for j in range(p):
+            tc = th.astype(np.complex128)
+            tc[j] += 1j * h
+            out = np.asarray(nonlinearity(tc.reshape(shape), x, t))
+            if not np.iscomplexobj(out):
+                return Jd
+            Jc[:, j] = np.imag(out).reshape(r) / h
+        if np.all(np.isfinite(Jc)) and np.max(np.abs(Jc - Jd)) <= 1e-5 * max(1.0, float(np.max(np.abs(Jd)))):
+            return Jc
+    except Exception:
+        pass
+    return Jd

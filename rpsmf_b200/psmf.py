@@ -32,7 +32,7 @@ import torch
 from . import _capi
 from .engine import FilterEngine
 from .learning_rate import BaseLearningRate, ConstantLearningRate
-from .nonlinearities import classify, jacobian_x
+from .nonlinearities import classify, jacobian_theta, jacobian_x
 
 _HOOKS = ("inner", "_predictive_mean", "_predictive_covariance", "_predict_measurement", "_compute_eta_k",
           "_compute_dictionary_innovation", "_update_dictionary_mean", "_update_dictionary_covariance",
@@ -182,7 +182,7 @@ class PSMFIter:
         ysl = Yd[k_first - 1:k_last]
         msl = None if Md is None else Md[k_first - 1:k_last]
         if self._dyn == _capi.DYN_EXTERNAL:
-            Yrec = self._sweep_external(eng, ysl, msl, theta, k_first, n)
+            Yrec = self._sweep_external(eng, ysl, msl, theta, k_first, n)     # accumulates self._gradsum itself
             grad = None
         else:
             out = eng.run(ysl, msl, k0=k_first, want_X=False, want_Yrec=True,
@@ -213,13 +213,19 @@ class PSMFIter:
     def _sweep_external(self, eng, ysl, msl, theta, k_first, n):
         """Arbitrary callable dynamics: x_bar and F = df/dx from the host, one step per launch."""
         Yrec = torch.empty((n, self._d), dtype=self._dtype, device=eng.device)
+        learn = np.asarray(theta).size > 0
         for j in range(n):
             k = k_first + j
             x = eng.get_state(want_C=False)["x"].cpu().numpy().reshape(self._r, 1)
             xbar = np.asarray(self.nonlinearity(theta, x, k), dtype=np.float64).reshape(self._r)
             F = None if self._simplified else jacobian_x(self.nonlinearity, theta, x, k)
-            eng.run(ysl[j:j + 1], None if msl is None else msl[j:j + 1], k0=k, want_X=False, Yrec_out=Yrec[j:j + 1],
-                    xbar=xbar, F=F)
+            out = eng.run(ysl[j:j + 1], None if msl is None else msl[j:j + 1], k0=k, want_X=False, Yrec_out=Yrec[j:j + 1],
+                          xbar=xbar, F=F, want_grad=learn)
+            if learn:
+                # d ell_k / d theta = J_theta' d ell_k / d f  (psmf.py:167-177): the kernel returns d ell_k / d f
+                gf = out["grad"].cpu().numpy().reshape(self._r)
+                J = jacobian_theta(self.nonlinearity, theta, x, k)
+                self._gradsum = self._gradsum + (J.T @ gf).reshape(self._gradsum.shape)
         return Yrec
 
     def _lambda_entering(self, k0):

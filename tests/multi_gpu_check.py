@@ -5,7 +5,14 @@
 
 Every rank filters its row shard; statistics are exchanged through the NVLink mailboxes inside the kernel.
 Checks: x_t identical (bitwise) on all ranks, and x_t / C / P / V within 1e-9 of the oracle run on all rows.
+
+    --same-device   all ranks share cuda:0 (process group on gloo; the kernels of the ranks time-slice on the GPU and
+                    reach each other's mailboxes through CUDA IPC): the N > 1 CUDA path on a one-GPU box
+    --quick         small cases only (the same-device mode pays a context switch per exchanged step)
+    --desert RANK   rank RANK connects and then leaves without filtering: the survivors' bounded waits must expire and
+                    psmf_status must report PSMF_E_STATE instead of hanging (set PSMF_SPIN_TIMEOUT_MS to keep it short)
 """
+import argparse
 import os
 import sys
 
@@ -27,11 +34,29 @@ def rel(a, b):
 
 
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--same-device", action="store_true")
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--desert", type=int, default=-1)
+    args = ap.parse_args()
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(lr)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    if args.same_device:
+        lr = 0
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(lr)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    if args.desert >= 0:
+        return desert(args, rank, world, lr)
     ok = True
-    for (d, r, T, kernel) in [(6400, 16, 30, 0), (100000, 16, 12, 2), (5000, 8, 20, 1), (777, 3, 25, 0)]:
+    # (d, r, T, kernel): kernel 0 = automatic.  1888 rows = 59 tiles: 29 / 30 tiles on two ranks straddle the automatic
+    # threshold of the TMA-staged kernel; 100008 rows leave the last rank a shard with d % 16 != 0 (not eligible):
+    # the ranks must agree on ONE kernel (psmf_mailbox_connect), whatever each would pick on its own
+    cases = [(6400, 16, 30, 0), (100000, 16, 12, 2), (5000, 8, 20, 1), (777, 3, 25, 0), (1888, 16, 20, 0), (100008, 16, 10, 0)]
+    if args.quick:
+        cases = [(1888, 16, 8, 0), (3840, 16, 8, 2), (777, 3, 10, 0)]
+    for (d, r, T, kernel) in cases:
         Y, M, C0, x0 = make_problem(d, r, T, seed=d)
         init = impute_init(r)
         b, e = shard_rows(d, world, rank)
@@ -62,6 +87,32 @@ def main():
         dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
+
+
+def desert(args, rank, world, lr):
+    """Failure detection: one rank disappears after the mailboxes are connected."""
+    from rpsmf_b200 import _capi
+    d, r, T = 6400, 16, 10
+    Y, M, C0, x0 = make_problem(d, r, T, seed=1)
+    init = impute_init(r)
+    b, e = shard_rows(d, world, rank)
+    eng = FilterEngine(e - b, r, robust=True, device=lr, d_global=d, world_size=world, rank=rank)
+    eng.connect(dist)
+    if rank == args.desert:
+        print("rank %d deserts" % rank, flush=True)
+        dist.barrier()
+        os._exit(0)
+    eng.set_state(C_=C0[b:e], V=init["V"], P=init["P"], x=x0, Q=init["Q"], rho=[init["rho"]], lam=[init["lam"]])
+    eng.run(torch.as_tensor(np.ascontiguousarray(Y[:, b:e])).cuda(lr), torch.as_tensor(np.ascontiguousarray(M[:, b:e])).cuda(lr))
+    dist.barrier()
+    try:
+        eng.status()
+        print("rank %d: FAIL, no error reported" % rank, flush=True)
+        os._exit(1)
+    except _capi.PsmfError as ex:
+        good = ex.code == -4 and "no progress" in str(ex)
+        print("rank %d: %s -> %s" % (rank, ex, "OK" if good else "FAIL"), flush=True)
+        os._exit(0 if good else 1)
 
 
 if __name__ == "__main__":

@@ -235,6 +235,48 @@ def test_very_large_shards(d, kernel):
     assert relerr(a[0], ref["X"]) < TOL and relerr(a[3]["C"], ref["C"]) < TOL and relerr(a[3]["V"], ref["V"]) < TOL
 
 
+def test_zero_initial_state_both_kernels():
+    """x0 = 0 with random-walk dynamics (a Beijing-style init): a = xbar'V xbar = 0 at step 0, so w0 = 1/a = inf.
+    Without missing rows the reference stays finite (Rbar = R + 0); both kernels must as well and agree with the
+    oracle (the pipelined kernel builds s from q1 and q0 and must not form inf * 0)."""
+    d, r, T = 3840, 16, 10
+    Y, _, C0, _ = make_problem(d, r, T, seed=31, missing=0.0)
+    x0 = np.zeros(r)
+    init = impute_init(r)
+    ref = _oracle_run(Y, None, C0, x0, init, po.OracleConfig(robust=True))
+    assert np.isfinite(ref[1]).all()
+    for kernel in (1, 2):
+        res = _engine_run(d, r, Y, None, C0, x0, init, True, kernel=kernel)
+        assert np.isfinite(res[0]).all() and np.isfinite(res[2]).all()
+        _compare(res, ref, TOL)
+
+
+def test_nearly_noise_free_data_kernels_agree():
+    """The pipelined kernel rebuilds q1 = gamma - 2 xbar'h + xbar'A xbar from raw second moments; on a fit whose
+    residual is far below the signal this cancels (relative accuracy of q1 ~ eps * gamma / q1).  Documented limit:
+    q1 is clamped at 0, everything stays finite, and the two kernels still agree far better than the data noise."""
+    d, r, T = 7680, 8, 30
+    rng = np.random.RandomState(5)
+    Ct = rng.randn(d, r)
+    x = rng.randn(r)
+    Y = np.zeros((T, d))
+    for t in range(T):
+        x = x + 0.1 * rng.randn(r)
+        Y[t] = Ct @ x + 1e-7 * rng.randn(d)
+    M = (rng.rand(T, d) >= 0.2).astype(np.uint8)
+    Y = Y * M
+    init = impute_init(r)
+    x0 = x - 0.1 * rng.randn(r)
+    a = _engine_run(d, r, Y, M, Ct, x0, init, True, kernel=1)
+    b = _engine_run(d, r, Y, M, Ct, x0, init, True, kernel=2)
+    assert a[4]["kernel"] == "direct" and b[4]["kernel"] == "tma"
+    for res in (a, b):
+        assert np.isfinite(res[0]).all() and np.isfinite(res[2]).all() and np.isfinite(res[3]["C"]).all()
+        assert (res[2][:, 3] > 0).all() and (res[2][:, 4] > 0).all()          # omega, phi
+    assert relerr(b[0], a[0]) < 1e-6 and relerr(b[3]["C"], a[3]["C"]) < 1e-6
+    _compare(a, _oracle_run(Y, M, Ct, x0, init, po.OracleConfig(robust=True)), TOL)
+
+
 def test_fp32_storage():
     torch = _torch()
     d, r, T = 600, 16, 40

@@ -95,3 +95,29 @@ def test_row_sharded_filter_two_gpus():
            "--master-port", "29511", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def _torchrun(nproc, port, *extra, env=None, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py")] + list(extra)
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=e)
+
+
+@pytest.mark.gpu
+def test_row_sharded_filter_two_ranks_one_gpu():
+    """The N > 1 CUDA path where only ONE GPU is leased: two ranks share cuda:0, their persistent kernels time-slice
+    on the device and exchange the statistics through each other's mailboxes (CUDA IPC).  Same checks as the
+    multi-GPU run: bit-identical replicas, 1e-9 against the unsharded oracle, one collectively chosen kernel."""
+    r = _torchrun(2, 29513, "--same-device", "--quick", env={"PSMF_SPIN_TIMEOUT_MS": "60000"})
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("OK") >= 6 and "FAIL" not in r.stdout
+
+
+@pytest.mark.gpu
+def test_deserting_rank_times_out_instead_of_hanging():
+    """A rank that dies after connecting must not hang the others: the bounded waits expire, the launch drains and
+    psmf_status returns PSMF_E_STATE."""
+    r = _torchrun(2, 29514, "--same-device", "--desert", "1", env={"PSMF_SPIN_TIMEOUT_MS": "1500"}, timeout=180)
+    assert "rank 0:" in r.stdout and "OK" in r.stdout and "FAIL" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
