@@ -50,11 +50,34 @@ typedef struct psmf_engine* psmf_handle;
 #define PSMF_FIXED_LAMBDA  16  /* rpsmf.py:36-40 */
 #define PSMF_LL_STUDENT    32  /* theta gradient of the Student-t incremental likelihood (rpsmf.py:62-71); unset: Gaussian
                                * form (psmf.py:57-64; with a mask: rpsmf.py:196-200)                                   */
+#define PSMF_NAN_MASK      64  /* missing entries of Y are NaN (the raw data form, rPSMF.py:160-164) and io->M must be NULL:
+                               * m = !isnan(y), y := 0 where missing (== rPSMF.py:198-202 done on the fly; no mask stream) */
 
 /* dynamics f_theta(x, k) of the predict half (psmf.py:104-115) */
 #define PSMF_DYN_IDENTITY 0    /* RandomWalk, nonlinearities.py:42-56; Impute scripts */
 #define PSMF_DYN_COS      1    /* cos(2 pi theta k + x), synthetic_psmf.py:105-106 */
+#define PSMF_DYN_LINEAR   2    /* x_bar = A x + c, F = A (psmf.py:104-115 with a linear f; ExperimentChange/PSMF.m:29-30):
+                                * A, c from psmf_set_linear_dynamics                                          */
 #define PSMF_DYN_EXTERNAL 3    /* x_bar and F = df/dx supplied by the caller, one step per psmf_run */
+
+/* kernels (psmf_config.kernel; psmf_launch_info2 reports the one that ran) */
+#define PSMF_KERNEL_AUTO   0
+#define PSMF_KERNEL_DIRECT 1   /* direct-load kernel: any shape */
+#define PSMF_KERNEL_STREAM 2   /* TMA-staged, software-pipelined kernel: one large series */
+#define PSMF_KERNEL_BATCH  3   /* resident batch kernel: one CTA per series, C in shared memory for the whole launch */
+
+/* statistics exchange between the GPUs that share one series by rows (psmf_config.exchange) */
+#define PSMF_XCHG_NVLINK   0   /* inside the kernel: peer stores into NVLink mailboxes (psmf_mailbox_*) */
+#define PSMF_XCHG_EXTERNAL 1   /* by the caller: psmf_run (one step) leaves the statistics of this GPU's rows in the
+                                * buffer of psmf_stats_buffer; the caller all-reduces (sum) it in place on the same
+                                * stream -- ncclAllReduce, MPI, anything -- and calls psmf_run_finish.  The NCCL
+                                * baseline of bench.py, and the way to shard a series across nodes.              */
+
+/* fused evaluation record written to eval_out: (n_series, PSMF_NEVAL) float64 (common.py:79-94) */
+#define PSMF_NEVAL 4
+#define PSMF_EVAL_SSE    0   /* sum over E of (y_hat - y_orig)^2   -> Epred = sqrt(SSE / COUNT), rPSMF.py:139 */
+#define PSMF_EVAL_INSIDE 1   /* entries of E with y_orig inside y_hat -+ sig sqrt(U)  (rPSMF.py:121-123, common.py:87-94) */
+#define PSMF_EVAL_COUNT  2   /* entries of E */
 
 /* error codes */
 #define PSMF_OK          0
@@ -86,9 +109,11 @@ typedef struct psmf_config {
     int32_t world_size; /* GPUs sharing ONE series by rows (1 = no exchange)                       */
     int32_t rank;
     int32_t ctas;       /* CTAs per series, 0 = auto                                                */
-    int32_t kernel;     /* 0 = auto, 1 = direct-load kernel, 2 = TMA-staged kernel (error if not eligible)  */
+    int32_t kernel;     /* PSMF_KERNEL_* (error if the forced kernel is not eligible for the shape)         */
     double  alpha;      /* V scale (rpsmf.py:45-51), 1.0 unless use_scaling                        */
     double  beta;       /* P scale                                                                  */
+    int32_t exchange;   /* PSMF_XCHG_* (world_size > 1)                                             */
+    int32_t reserved;   /* 0                                                                        */
 } psmf_config;
 
 typedef struct psmf_io {
@@ -106,7 +131,16 @@ typedef struct psmf_io {
     const double*  xbar_ext;   /* PSMF_DYN_EXTERNAL: (n_series, r)                                    */
     const double*  F_ext;      /* PSMF_DYN_EXTERNAL: (n_series, r, r) row-major                       */
     double*        grad_out;   /* (n_series, r) sum over the run of d ell_k / d theta (PSMF_DYN_COS), or NULL
-                                * (_store_gradient, psmf.py:167-177)                                     */
+                                * (_store_gradient, psmf.py:167-177); PSMF_DYN_EXTERNAL: d ell_k / d f of the one step */
+    /* fused evaluation (all NULL / 0 = off): RMSE of the one-step predictions over the entries marked in E and the
+     * number of original values inside the sig-sigma interval, accumulated in the row pass -- no (n, d) Yrec /
+     * YrecL / YrecH arrays (rPSMF.py:67-69,121-123,139; common.py:79-94).  Direct-load and batch kernels only. */
+    const void*    Yorig;      /* (n_series, n_steps, ldy) original values, same strides as Y (YorigInt)   */
+    const uint8_t* E;          /* (n_series, n_steps, lde) 1 = evaluate here (Mmiss)                      */
+    int64_t        lde;
+    int64_t        e_series_stride;
+    double         sig;        /* interval half-width in sigmas                                          */
+    double*        eval_out;   /* (n_series, PSMF_NEVAL) sums over THIS run                              */
 } psmf_io;
 
 /* lifecycle ------------------------------------------------------------------------------------ */
@@ -127,6 +161,40 @@ int  psmf_get_state(psmf_handle h, void* C, double* V, double* P, double* x,
  * nonlinearity for the first step; pypsmf counts from 1).                                           */
 int  psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k0, void* stream);
 
+/* PSMF_XCHG_EXTERNAL: the statistics vector of one step (device pointer owned by the library, `count` doubles) and
+ * the second half of a step (see PSMF_XCHG_EXTERNAL).  `io` and `k0` are those of the preceding psmf_run.       */
+int  psmf_stats_buffer(psmf_handle h, double** dev_ptr, int32_t* count);
+int  psmf_run_finish(psmf_handle h, const psmf_io* io, int64_t k0, void* stream);
+
+/* PSMF_DYN_LINEAR: A (r, r) row-major and c (r) or NULL, device pointers, copied. One A per engine (all series). */
+int  psmf_set_linear_dynamics(psmf_handle h, const double* A, const double* c, void* stream);
+
+/* forecast (PSMFIter.predict, psmf.py:182-188): roll x through the dynamics for n_pred steps from the engine's
+ * current state (absolute index of the first forecast step = k0) and emit C x.  Xpred_in (n_series, n_pred, r)
+ * replaces the roll-out (PSMF_DYN_EXTERNAL: the caller owns f); Xpred_out (n_series, n_pred, r) and Ypred_out
+ * (n_series, n_pred, ldp) in the engine dtype may be NULL.                                                 */
+int  psmf_predict(psmf_handle h, int64_t n_pred, int64_t k0, const double* Xpred_in, double* Xpred_out, void* Ypred_out,
+                  int64_t ldp, int64_t pred_series_stride, void* stream);
+
+/* Efull of the imputation experiment (rPSMF.py:137-140): over the entries marked in E, the sum of
+ * (C X - Yorig)^2 with the engine's CURRENT C and the filtered X (n_series, n_steps, r) of the sweep, and their
+ * number -> out (n_series, 2).  No (d, n) product is materialised.                                         */
+int  psmf_eval_full(psmf_handle h, const double* X, int64_t n_steps, const void* Yorig, int64_t ldy, int64_t y_series_stride,
+                    const uint8_t* E, int64_t lde, int64_t e_series_stride, double* out, void* stream);
+
+/* ingest (rPSMF.py:160-164,198-202): src (d, n) row-major float64 on the device with NaN = missing -> time-major
+ * Y_out (n, ldy) of `dtype` (NaN kept if keep_nan, else zero-filled) and / or M_out (n, ldm) with 1 = observed.  */
+int  psmf_ingest(int32_t device, const double* src, int64_t d, int64_t n, int32_t dtype, int32_t keep_nan, void* Y_out, int64_t ldy,
+                 uint8_t* M_out, int64_t ldm, void* stream);
+/* (d, n) row-major bytes -> time-major (n, ld) bytes, 1 where non-zero (M, Mmiss narrowed to one byte by the host) */
+int  psmf_transpose_mask(int32_t device, const uint8_t* src, int64_t d, int64_t n, uint8_t* dst, int64_t ld, void* stream);
+/* one sweep of prepare_missing (common.py:66-75) on time-major NaN-encoded Y (n, ldy): row i loses the `seg` entries
+ * from starts[i] on that are not NaN yet (Y <- NaN, E <- 1); *count_dev += entries removed.  psmf_count_nan gives
+ * NumMissDefault (common.py:65).  starts: d int64 on the device, drawn by the caller's generator.                */
+int  psmf_missing_segments(int32_t device, int32_t dtype, void* Y, int64_t ldy, uint8_t* E, int64_t lde, int64_t d, int64_t n,
+                           const int64_t* starts, int32_t seg, uint64_t* count_dev, void* stream);
+int  psmf_count_nan(int32_t device, int32_t dtype, const void* Y, int64_t ldy, int64_t d, int64_t n, uint64_t* count_dev, void* stream);
+
 /* synchronise the stream of the last run and report the device status word:
  * *first_bad_step = -1 if every step produced finite N/omega/phi, else the first offending step.
  * Returns PSMF_E_STATE (text in psmf_last_error) if a wait inside the kernel expired -- a peer GPU or CTA stopped
@@ -135,8 +203,8 @@ int  psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k0, voi
 int  psmf_status(psmf_handle h, int64_t* first_bad_step);
 
 /* introspection used by bench.py / tests, describing the last psmf_run: CTAs per series, threads per CTA,
- * dynamic smem bytes, kernels launched, which kernel ran (1 direct-load, 2 TMA-staged) and its
- * shared-memory chunk slots (0 for kernel 1).                                                        */
+ * dynamic smem bytes, kernels launched, which kernel ran (PSMF_KERNEL_*) and, for the TMA-staged kernel, its
+ * shared-memory chunk slots and whether C stayed resident in shared memory.                          */
 int  psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* smem_bytes, int32_t* launches);
 int  psmf_launch_info2(psmf_handle h, int32_t* kernel, int32_t* nslot, int32_t* resident);
 

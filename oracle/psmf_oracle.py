@@ -44,6 +44,7 @@ import numpy as np
 # dynamics ids shared with include/psmf_b200.h
 DYN_IDENTITY = 0      # pypsmf/psmf/nonlinearities.py:42-56  (RandomWalk)
 DYN_COS = 1           # ExperimentSynthetic/synthetic_psmf.py:105-106
+DYN_LINEAR = 2        # x_bar = A x + c, F = A (psmf.py:104-115 with a linear f; ExperimentChange/PSMF.m:29-30)
 DYN_EXTERNAL = 3      # xbar and F supplied by the caller for every step
 
 
@@ -60,6 +61,8 @@ class OracleConfig:
     sig: float = 2.0
     dynamics: int = DYN_IDENTITY
     d_global: int | None = None  # denominator d (differs from local rows only when sharded)
+    lin_A: np.ndarray | None = None   # DYN_LINEAR
+    lin_c: np.ndarray | None = None
 
 
 @dataclasses.dataclass
@@ -69,21 +72,27 @@ class OracleState:
     P: np.ndarray        # (r, r)
     V: np.ndarray        # (r, r)
     Q: np.ndarray        # (r, r)
-    rho: float           # R = rho * I_d  (uniform diagonal; every experiment uses this)
+    rho: float           # R = rho * I_d (float: uniform diagonal, every experiment uses this) or a (d,) vector = diag(R)
     lam: float
     theta: np.ndarray | None = None
 
     def copy(self) -> "OracleState":
         return OracleState(
             self.C.copy(), self.x.copy(), self.P.copy(), self.V.copy(),
-            self.Q.copy(), float(self.rho), float(self.lam),
+            self.Q.copy(), float(self.rho) if np.ndim(self.rho) == 0 else np.array(self.rho, dtype=np.float64), float(self.lam),
             None if self.theta is None else self.theta.copy(),
         )
 
 
-def dynamics(kind: int, theta, x, k):
+def dynamics(kind: int, theta, x, k, cfg=None):
     """Return (xbar, F) with F = d f / d x   (psmf.py:104-115)."""
     r = x.shape[0]
+    if kind == DYN_LINEAR:
+        A = np.asarray(cfg.lin_A, dtype=np.float64)
+        xb = A @ x
+        if cfg.lin_c is not None:
+            xb = xb + np.asarray(cfg.lin_c, dtype=np.float64).reshape(-1)
+        return xb, A
     if kind == DYN_IDENTITY:
         return x.copy(), np.eye(r)
     if kind == DYN_COS:
@@ -110,7 +119,13 @@ def local_stats(C, xbar, a, rho, y, m):
     q1 = float(np.sum(e[obs] ** 2))
     q0 = float(np.sum(e[~obs] ** 2))
     nobs = float(np.sum(m))
-    return yhat, e, dict(G=G, b=b, s=s, q1=q1, q0=q0, nobs=nobs)
+    S = dict(G=G, b=b, s=s, q1=q1, q0=q0, nobs=nobs)
+    if np.ndim(rho) != 0:
+        # non-uniform diagonal R: the unweighted Gram and sum m_i rho_i are needed for eta (rPSMF.py:95,108), and phi
+        # needs sum e_i^2 / (a m_i + eta) -- with a per-row mask only, so q1 / q0 still suffice (rPSMF.py:112-114)
+        S["G0"] = C.T @ (m[:, None] * C)
+        S["nrho"] = float(np.sum(m * rho))
+    return yhat, e, S
 
 
 def small_update(st: OracleState, cfg: OracleConfig, xbar, F, vx, vxt, a, S, d):
@@ -123,15 +138,18 @@ def small_update(st: OracleState, cfg: OracleConfig, xbar, F, vx, vxt, a, S, d):
         K = None
         x_new = xbar.copy()                           # synthetic_psmf.py:93-94
         sSe = s                                       # synthetic_rpsmf.py:93-98 (S^-1 = Rbar^-1)
-        eta = rho                                     # tr(R)/d, synthetic_psmf.py:86-87
+        eta = float(np.mean(rho))                     # tr(R)/d, synthetic_psmf.py:86-87
     else:
         Pbar = F @ st.P @ F.T + st.Q                  # rPSMF.py:87 / psmf.py:115
         K = np.linalg.solve(np.eye(r) + Pbar @ G, Pbar)
         Kb = K @ b
         x_new = xbar + Kb                             # rPSMF.py:104
         sSe = s - float(b @ Kb)                       # diff' CPinv diff, rPSMF.py:105
-        G0 = (rho + a) * G                            # unweighted Gram (uniform rho)
-        eta = (rho * nobs + float(np.sum(Pbar * G0))) / d     # rPSMF.py:108
+        if "G0" in S:                                 # non-uniform diagonal R
+            eta = (S["nrho"] + float(np.sum(Pbar * S["G0"]))) / d        # rPSMF.py:108: trace(M R M + CM PP CM') / d
+        else:
+            G0 = (rho + a) * G                        # unweighted Gram (uniform rho)
+            eta = (rho * nobs + float(np.sum(Pbar * G0))) / d     # rPSMF.py:108
     if cfg.robust:
         omega = (lam + sSe) / (lam + d)               # rPSMF.py:105
     else:
@@ -154,7 +172,7 @@ def small_update(st: OracleState, cfg: OracleConfig, xbar, F, vx, vxt, a, S, d):
     rho_new = omega * rho                             # rPSMF.py:134
     lam_new = lam if (cfg.fixed_lambda or not cfg.robust) else lam + d   # rPSMF.py:135
     g = (vx if cfg.c_update_transpose else vxt) / N   # rank-1 direction, rPSMF.py:111
-    scal = dict(a=a, eta=eta, N=N, omega=omega, phi=phi, sSe=sSe, lam=lam, rho=rho)
+    scal = dict(a=a, eta=eta, N=N, omega=omega, phi=phi, sSe=sSe, lam=lam, rho=float(np.mean(rho)))
     return x_new, P_new, V_new, Q_new, rho_new, lam_new, g, scal
 
 
@@ -167,7 +185,7 @@ def step(st: OracleState, cfg: OracleConfig, y, m, k=0, xbar_F=None):
     if xbar_F is not None:
         xbar, F = xbar_F
     else:
-        xbar, F = dynamics(cfg.dynamics, st.theta, st.x, k)
+        xbar, F = dynamics(cfg.dynamics, st.theta, st.x, k, cfg)
     vx = st.V @ xbar
     vxt = st.V.T @ xbar
     a = float(xbar @ vx)                              # rPSMF.py:93
@@ -239,10 +257,11 @@ def impute_fit(Y, C, X, M, Mmiss, V, Q0, rho0, P, lam0, sig, Iter, YorigInt, Ein
     Epred = np.zeros((1, Iter + 1)); Efull = np.zeros((1, Iter + 1))
     Epred[:, 0] = Einit; Efull[:, 0] = Einit
     Yrec = np.zeros((d, n)); lo = np.zeros((d, n)); hi = np.zeros((d, n))
-    st = OracleState(C.copy(), X[:, n - 1].copy(), P.copy(), V.copy(), Q0.copy(), float(rho0), float(lam0))
+    rho_of = (lambda: float(rho0)) if np.ndim(rho0) == 0 else (lambda: np.array(rho0, dtype=np.float64))
+    st = OracleState(C.copy(), X[:, n - 1].copy(), P.copy(), V.copy(), Q0.copy(), rho_of(), float(lam0))
     Mf = M.astype(np.float64)
     for i in range(Iter):
-        st.Q = Q0.copy(); st.rho = float(rho0); st.lam = float(lam0)      # rPSMF.py:77-79
+        st.Q = Q0.copy(); st.rho = rho_of(); st.lam = float(lam0)         # rPSMF.py:77-79
         st.x = X[:, n - 1].copy()                                          # rPSMF.py:86 wrap-around
         for t in range(n):
             st, out = step(st, cfg, Y[:, t], Mf[:, t])
@@ -277,3 +296,15 @@ def theta_grad_cos(robust, theta, mu_prev, k, y, C, V, eta, lam, d):
     e = y - C @ f
     g_f = dll_df(robust, f, V, C.T @ e, float(e @ e), eta, lam, d)
     return g_f * (-np.sin(arg)) * (2.0 * np.pi * k)
+
+
+def predict(st: OracleState, cfg: OracleConfig, T, n_pred):
+    """PSMFIter.predict (psmf.py:182-188): roll mu through f for n_pred steps from the filtered state at T and emit
+    C mu.  Returns (mu_pred (n_pred, r), y_pred (n_pred, d))."""
+    x = st.x.copy()
+    mus = []
+    for k in range(T + 1, T + n_pred + 1):
+        x, _ = dynamics(cfg.dynamics, st.theta, x, k, cfg)
+        mus.append(x.copy())
+    mus = np.stack(mus)
+    return mus, mus @ st.C.T

@@ -9,8 +9,8 @@ Python surface of the reference kept for the filter hot path:
 All arithmetic runs in hand-written sm_100a CUDA (libpsmf_b200.so, C ABI in include/psmf_b200.h).
 """
 
-from .engine import FilterEngine  # noqa: F401
-from .experiment import prepare_missing, run_impute_experiment  # noqa: F401
+from .engine import FilterEngine, count_nan, ingest, missing_segments, transpose_mask  # noqa: F401
+from .experiment import prepare_missing, prepare_missing_device, run_impute_experiment  # noqa: F401
 from .impute import ProbabilisticSequentialMatrixFactorizer, robust_PSMF  # noqa: F401
 from .psmf import PSMFIter, PSMFIterMissing, PSMFRecursive  # noqa: F401
 from .rpsmf import rPSMFIter, rPSMFIterMissing, rPSMFRecursive  # noqa: F401
@@ -27,4 +27,10 @@ def shard_rows(d, world_size, rank):
     return b, e
 
 
-__version__ = "0.1.0"
+def shard_series(n_series, world_size, rank):
+    """Series [begin, end) owned by `rank` when a batch of independent series (or restarts) is split over
+    `world_size` GPUs: no communication between them (BASELINE.json configs[4])."""
+    return (n_series * rank) // world_size, (n_series * (rank + 1)) // world_size
+
+
+__version__ = "0.2.0"

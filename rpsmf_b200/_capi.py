@@ -14,9 +14,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpsmf_b200.so")
 
 F64, F32 = 0, 1
-ROBUST, SIMPLIFIED, CUPDATE_VT, FIXED_LAMBDA, LL_STUDENT = 1, 2, 4, 16, 32
-DYN_IDENTITY, DYN_COS, DYN_EXTERNAL = 0, 1, 3
+ROBUST, SIMPLIFIED, CUPDATE_VT, FIXED_LAMBDA, LL_STUDENT, NAN_MASK = 1, 2, 4, 16, 32, 64
+DYN_IDENTITY, DYN_COS, DYN_LINEAR, DYN_EXTERNAL = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STREAM, KERNEL_BATCH = 0, 1, 2, 3
+XCHG_NVLINK, XCHG_EXTERNAL = 0, 1
 NSCAL = 8
+NEVAL = 4
+EVAL_SSE, EVAL_INSIDE, EVAL_COUNT = 0, 1, 2
 MAILBOX_BLOB_BYTES = 128
 SCAL_NAMES = ("a", "eta", "N", "omega", "phi", "sSe", "lam", "rho")
 
@@ -24,6 +28,8 @@ SCAL_NAMES = ("a", "eta", "N", "omega", "phi", "sSe", "lam", "rho")
 EXPORTS = (
     "psmf_create", "psmf_destroy", "psmf_last_error", "psmf_version", "psmf_set_state", "psmf_get_state",
     "psmf_run", "psmf_status", "psmf_launch_info", "psmf_launch_info2", "psmf_set_trace", "psmf_mailbox_export", "psmf_mailbox_connect",
+    "psmf_stats_buffer", "psmf_run_finish", "psmf_set_linear_dynamics", "psmf_predict", "psmf_eval_full", "psmf_ingest",
+    "psmf_transpose_mask", "psmf_missing_segments", "psmf_count_nan",
 )
 
 
@@ -32,7 +38,7 @@ class PsmfConfig(C.Structure):
         ("d", C.c_int64), ("d_global", C.c_int64), ("r", C.c_int32), ("n_series", C.c_int32),
         ("dtype", C.c_int32), ("flags", C.c_int32), ("dynamics", C.c_int32), ("device", C.c_int32),
         ("world_size", C.c_int32), ("rank", C.c_int32), ("ctas", C.c_int32), ("kernel", C.c_int32),
-        ("alpha", C.c_double), ("beta", C.c_double),
+        ("alpha", C.c_double), ("beta", C.c_double), ("exchange", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -44,6 +50,8 @@ class PsmfIO(C.Structure):
         ("Yrec_out", C.c_void_p), ("ldrec", C.c_int64), ("rec_series_stride", C.c_int64),
         ("scal_out", C.c_void_p),
         ("xbar_ext", C.c_void_p), ("F_ext", C.c_void_p), ("grad_out", C.c_void_p),
+        ("Yorig", C.c_void_p), ("E", C.c_void_p), ("lde", C.c_int64), ("e_series_stride", C.c_int64), ("sig", C.c_double),
+        ("eval_out", C.c_void_p),
     ]
 
 
@@ -80,6 +88,15 @@ def lib():
     L.psmf_set_trace.argtypes = [vp, vp, i32]
     L.psmf_mailbox_export.argtypes = [vp, vp]
     L.psmf_mailbox_connect.argtypes = [vp, vp, i32]
+    L.psmf_stats_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
+    L.psmf_run_finish.argtypes = [vp, C.POINTER(PsmfIO), i64, vp]
+    L.psmf_set_linear_dynamics.argtypes = [vp, vp, vp, vp]
+    L.psmf_predict.argtypes = [vp, i64, i64, vp, vp, vp, i64, i64, vp]
+    L.psmf_eval_full.argtypes = [vp, vp, i64, vp, i64, i64, vp, i64, i64, vp, vp]
+    L.psmf_ingest.argtypes = [i32, vp, i64, i64, i32, i32, vp, i64, vp, i64, vp]
+    L.psmf_transpose_mask.argtypes = [i32, vp, i64, i64, vp, i64, vp]
+    L.psmf_missing_segments.argtypes = [i32, i32, vp, i64, vp, i64, i64, i64, vp, i32, vp, vp]
+    L.psmf_count_nan.argtypes = [i32, i32, vp, i64, i64, i64, vp, vp]
     for name in EXPORTS:
         if name not in ("psmf_last_error",):
             getattr(L, name).restype = C.c_int

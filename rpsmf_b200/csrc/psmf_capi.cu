@@ -8,6 +8,7 @@
 
 #include "../../include/psmf_b200.h"
 #include "psmf_common.cuh"
+#include "psmf_tools.cuh"
 
 PSMF_DECLARE_R(1) PSMF_DECLARE_R(2) PSMF_DECLARE_R(3) PSMF_DECLARE_R(4)
 PSMF_DECLARE_R(5) PSMF_DECLARE_R(6) PSMF_DECLARE_R(7) PSMF_DECLARE_R(8)
@@ -28,6 +29,19 @@ static const shape_fn SHAPE_S[MAXR + 1] = {
     nullptr,          shape_stream_r1,  shape_stream_r2,  shape_stream_r3,  shape_stream_r4,  shape_stream_r5,
     shape_stream_r6,  shape_stream_r7,  shape_stream_r8,  shape_stream_r9,  shape_stream_r10, shape_stream_r11,
     shape_stream_r12, shape_stream_r13, shape_stream_r14, shape_stream_r15, shape_stream_r16};
+static const launch_fn LAUNCH_B[MAXR + 1] = {
+    nullptr,          launch_batch_r1,  launch_batch_r2,  launch_batch_r3,  launch_batch_r4,  launch_batch_r5,
+    launch_batch_r6,  launch_batch_r7,  launch_batch_r8,  launch_batch_r9,  launch_batch_r10, launch_batch_r11,
+    launch_batch_r12, launch_batch_r13, launch_batch_r14, launch_batch_r15, launch_batch_r16};
+static const shape_fn SHAPE_B4[MAXR + 1] = {
+    nullptr,          shape_batch4_r1,  shape_batch4_r2,  shape_batch4_r3,  shape_batch4_r4,  shape_batch4_r5,
+    shape_batch4_r6,  shape_batch4_r7,  shape_batch4_r8,  shape_batch4_r9,  shape_batch4_r10, shape_batch4_r11,
+    shape_batch4_r12, shape_batch4_r13, shape_batch4_r14, shape_batch4_r15, shape_batch4_r16};
+static const shape_fn SHAPE_B8[MAXR + 1] = {
+    nullptr,          shape_batch8_r1,  shape_batch8_r2,  shape_batch8_r3,  shape_batch8_r4,  shape_batch8_r5,
+    shape_batch8_r6,  shape_batch8_r7,  shape_batch8_r8,  shape_batch8_r9,  shape_batch8_r10, shape_batch8_r11,
+    shape_batch8_r12, shape_batch8_r13, shape_batch8_r14, shape_batch8_r15, shape_batch8_r16};
+static size_t batch_dyn(int64_t ntiles, int R, size_t esize, bool eval) { return batch_dyn_bytes(ntiles, R, esize, eval); }
 static const shape_fn SHAPE[MAXR + 1] = {
     nullptr,          shape_filter_r1,  shape_filter_r2,  shape_filter_r3,  shape_filter_r4,  shape_filter_r5,
     shape_filter_r6,  shape_filter_r7,  shape_filter_r8,  shape_filter_r9,  shape_filter_r10, shape_filter_r11,
@@ -81,6 +95,18 @@ struct psmf_engine {
     size_t dyn_smem2 = 0;
     bool resident2 = false;
     int last_kernel = 0;
+    // resident batch kernel (one CTA per series, C in shared memory): available when the dictionary of a series fits
+    bool batch_ok = false, batch_nw8 = false;
+    int threads3 = 0;
+    size_t dyn_smem3 = 0, last_dyn = 0;
+    int maxsmem = 0;
+    double* eval_part = nullptr;       // [S][cps][NEVAL] per-CTA evaluation sums of a launch
+    double* stats_ext = nullptr;       // PSMF_XCHG_EXTERNAL: statistics of one step / residuals between the two launches
+    double* e_ext = nullptr;
+    double* lin = nullptr;             // PSMF_DYN_LINEAR: A (R * R) then c (R)
+    bool lin_set = false, lin_has_c = false;
+    double* tool_buf = nullptr;        // scratch of psmf_eval_full / psmf_predict
+    size_t tool_bytes = 0;
     unsigned long long* trace = nullptr;
     int trace_steps = 0;
     // NVLink mailbox (world_size > 1): [2 parities][MAX_PEERS][192] tagged 16-byte cells (psmf_filter.cuh gpu_exchange)
@@ -124,6 +150,11 @@ static void free_engine(psmf_engine* e) {
     cudaFree(e->bar);
     cudaFree(e->gparams);
     cudaFree(e->status);
+    cudaFree(e->eval_part);
+    cudaFree(e->stats_ext);
+    cudaFree(e->e_ext);
+    cudaFree(e->lin);
+    cudaFree(e->tool_buf);
     for (int i = 0; i < PSMF_MAX_PEERS; ++i)
         if (e->peer_mbox[i] && i != e->cfg.rank) cudaIpcCloseMemHandle(e->peer_mbox[i]);
     cudaFree(e->mbox);
@@ -137,8 +168,14 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     if (cfg->d < 1) return fail(nullptr, PSMF_E_INVALID, "d must be >= 1");
     if (cfg->n_series < 1) return fail(nullptr, PSMF_E_INVALID, "n_series must be >= 1");
     if (cfg->dtype != PSMF_F64 && cfg->dtype != PSMF_F32) return fail(nullptr, PSMF_E_INVALID, "dtype must be PSMF_F64 or PSMF_F32");
-    if (cfg->dynamics != PSMF_DYN_IDENTITY && cfg->dynamics != PSMF_DYN_COS && cfg->dynamics != PSMF_DYN_EXTERNAL)
+    if (cfg->dynamics != PSMF_DYN_IDENTITY && cfg->dynamics != PSMF_DYN_COS && cfg->dynamics != PSMF_DYN_EXTERNAL &&
+        cfg->dynamics != PSMF_DYN_LINEAR)
         return fail(nullptr, PSMF_E_INVALID, "unknown dynamics id");
+    if (cfg->kernel < 0 || cfg->kernel > 3) return fail(nullptr, PSMF_E_INVALID, "kernel must be PSMF_KERNEL_AUTO / DIRECT / STREAM / BATCH");
+    if (cfg->exchange != PSMF_XCHG_NVLINK && cfg->exchange != PSMF_XCHG_EXTERNAL)
+        return fail(nullptr, PSMF_E_INVALID, "exchange must be PSMF_XCHG_NVLINK or PSMF_XCHG_EXTERNAL");
+    if (cfg->exchange == PSMF_XCHG_EXTERNAL && cfg->n_series > 1)
+        return fail(nullptr, PSMF_E_INVALID, "PSMF_XCHG_EXTERNAL shards ONE series by rows (n_series must be 1)");
     if (cfg->world_size < 1 || cfg->world_size > PSMF_MAX_PEERS || cfg->rank < 0 || cfg->rank >= cfg->world_size)
         return fail(nullptr, PSMF_E_INVALID, "bad world_size / rank");
     if (cfg->world_size > 1 && cfg->n_series > 1)
@@ -161,6 +198,7 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
     cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     e->num_sms = sms;
+    e->maxsmem = maxsmem;
     if (const char* ev = getenv("PSMF_SPIN_TIMEOUT_MS")) {              // how long a kernel waits for a silent peer GPU / CTA
         const long long ms = atoll(ev);
         if (ms >= 1) e->spin_ns = (unsigned long long)ms * 1000000ULL;
@@ -199,7 +237,7 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     e->cooperative = cps > 1;
 
     // ---- TMA-staged kernel: slots of V2_TS tiles + y/m slices, residual buffer behind them ----
-    if (cfg->kernel != 1 && e->d % 16 == 0 && e->S == 1 && sms >= 2) {
+    if ((cfg->kernel == 0 || cfg->kernel == 2) && cfg->exchange == PSMF_XCHG_NVLINK && e->d % 16 == 0 && e->S == 1 && sms >= 2) {
         const int TS = V2_TS;
         auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
         const size_t slot = r128((size_t)TS * e->R * TILE * e->esize);     // psmf_stream.cuh SlotLayout: one chunk of C
@@ -246,6 +284,22 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
         free_engine(e);
         return fail(nullptr, PSMF_E_INVALID, "TMA-staged kernel not available for this shape (needs d % 16 == 0, one series, and room for a ring of 5 chunk slots)");
     }
+    // ---- resident batch kernel: one CTA per series, the whole dictionary of a series in shared memory ----
+    if ((cfg->kernel == 0 || cfg->kernel == 3) && cfg->world_size == 1) {
+        e->batch_nw8 = e->ntiles >= 8 && e->S <= 2 * sms;       // few series: more warps per series; many: more series per SM
+        e->dyn_smem3 = batch_dyn(e->ntiles, e->R, e->esize, false);
+        LaunchShape sb;
+        if (e->dyn_smem3 <= (size_t)maxsmem &&
+            (e->batch_nw8 ? SHAPE_B8 : SHAPE_B4)[e->R](cfg->dtype, e->dyn_smem3, &sb) == cudaSuccess && sb.max_ctas_per_sm >= 1) {
+            e->batch_ok = true;
+            e->threads3 = sb.threads;
+        }
+        cudaGetLastError();
+    }
+    if (cfg->kernel == 3 && !e->batch_ok) {
+        free_engine(e);
+        return fail(nullptr, PSMF_E_INVALID, "batch kernel not available: the dictionary of a series (d x r) must fit the shared memory of one CTA, world_size 1");
+    }
 
     const size_t cbytes = (size_t)e->S * e->ntiles * TILE * e->R * e->esize;
     const int nsp = (ngram(e->R) + 2 * e->R + 5 + 7) / 8 * 8;      // >= nstat_pad(R): pipelined statistics (nstat2_pad)
@@ -274,10 +328,19 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     CKC(cudaMalloc(&e->gparams, GPARAMS_BYTES));                        // 16-byte cells (psmf_stream.cuh): parameter sets [2][2R], totals [2][nstat2_pad]
     CKC(cudaMalloc(&e->status, sizeof(long long)));
     CKC(cudaMemset(e->status, 0xFF, sizeof(long long)));
-    if (cfg->world_size > 1) {
+    if (cfg->world_size > 1 && cfg->exchange == PSMF_XCHG_NVLINK) {
         CKC(cudaMalloc(&e->mbox, mbox_bytes()));
         CKC(cudaMemset(e->mbox, 0, mbox_bytes()));
     }
+    if (cfg->exchange == PSMF_XCHG_EXTERNAL) {
+        CKC(cudaMalloc(&e->stats_ext, (size_t)nstat_pad(MAXR) * sizeof(double)));
+        CKC(cudaMemset(e->stats_ext, 0, (size_t)nstat_pad(MAXR) * sizeof(double)));
+        CKC(cudaMalloc(&e->e_ext, (size_t)(e->ntiles + 1) * TILE * sizeof(double)));
+        CKC(cudaMemset(e->e_ext, 0, (size_t)(e->ntiles + 1) * TILE * sizeof(double)));
+    }
+    CKC(cudaMalloc(&e->eval_part, (size_t)e->S * (e->cps > 1 ? e->cps : 1) * NEVAL * sizeof(double)));
+    CKC(cudaMalloc(&e->lin, (size_t)(e->R * e->R + e->R) * sizeof(double)));
+    CKC(cudaMemset(e->lin, 0, (size_t)(e->R * e->R + e->R) * sizeof(double)));
 #undef CKC
     *out = e;
     return PSMF_OK;
@@ -341,17 +404,30 @@ extern "C" int psmf_get_state(psmf_handle h, void* C, double* V, double* P, doub
     return state_io(h, false, C, V, P, x, Q, rho, lambda, theta, (cudaStream_t)stream);
 }
 
-extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k0, void* stream) {
+static int run_impl(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k0, void* stream, int phase) {
     if (!h || !io) return PSMF_E_INVALID;
     if (n_steps < 1) return fail(h, PSMF_E_INVALID, "n_steps must be >= 1");
     if (!io->Y) return fail(h, PSMF_E_INVALID, "Y is NULL");
     if (io->ldy < h->d) return fail(h, PSMF_E_INVALID, "ldy < d");
     if (io->M && io->ldm < h->d) return fail(h, PSMF_E_INVALID, "ldm < d");
+    if (io->M && (h->cfg.flags & PSMF_NAN_MASK)) return fail(h, PSMF_E_INVALID, "PSMF_NAN_MASK: the mask is encoded in Y, M must be NULL");
     if (io->Yrec_out && io->ldrec < h->d) return fail(h, PSMF_E_INVALID, "ldrec < d");
+    const bool eval = io->E != nullptr;
+    if (eval && (!io->Yorig || !io->eval_out || io->lde < h->d))
+        return fail(h, PSMF_E_INVALID, "fused evaluation needs E (lde >= d), Yorig and eval_out together");
     if (h->cfg.dynamics == PSMF_DYN_EXTERNAL) {
         if (n_steps != 1) return fail(h, PSMF_E_INVALID, "PSMF_DYN_EXTERNAL runs one step per call");
         if (!io->xbar_ext || (!io->F_ext && !(h->cfg.flags & PSMF_SIMPLIFIED)))
             return fail(h, PSMF_E_INVALID, "PSMF_DYN_EXTERNAL needs xbar_ext and F_ext");
+    }
+    if (h->cfg.dynamics == PSMF_DYN_LINEAR && !h->lin_set)
+        return fail(h, PSMF_E_STATE, "PSMF_DYN_LINEAR: call psmf_set_linear_dynamics first");
+    const bool external = h->cfg.exchange == PSMF_XCHG_EXTERNAL;
+    if (external) {
+        if (n_steps != 1) return fail(h, PSMF_E_INVALID, "PSMF_XCHG_EXTERNAL runs one step per psmf_run / psmf_run_finish pair");
+        if (eval) return fail(h, PSMF_E_INVALID, "fused evaluation is not available with PSMF_XCHG_EXTERNAL");
+    } else if (phase != 0) {
+        return fail(h, PSMF_E_STATE, "psmf_run_finish needs an engine created with PSMF_XCHG_EXTERNAL");
     }
     cudaStream_t st = (cudaStream_t)stream;
     CK(h, cudaSetDevice(h->cfg.device));
@@ -379,10 +455,16 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
 #endif
     p.spin_ns = h->spin_ns;
     p.alpha = h->cfg.alpha; p.beta = h->cfg.beta;
-    p.world = h->cfg.world_size; p.rank = h->cfg.rank;
+    p.world = external ? 1 : h->cfg.world_size; p.rank = h->cfg.rank;
+    p.phase = phase;
+    p.stats_ext = h->stats_ext; p.e_ext = h->e_ext;
+    p.lin_A = h->lin; p.lin_c = h->lin_has_c ? h->lin + h->R * h->R : nullptr;
+    if (eval) {
+        p.Yorig = io->Yorig; p.E = io->E; p.lde = io->lde; p.esst = io->e_series_stride; p.sig = io->sig;
+        p.eval_part = h->eval_part;
+    }
     if (p.world > 1) {
         if (!h->connected) return fail(h, PSMF_E_STATE, "world_size > 1: call psmf_mailbox_connect before psmf_run");
-        // the mailbox slots are nstat_pad(R) doubles apart (kernel indexing), inside a buffer sized for MAXR
         p.mbox_local = (double*)h->mbox;
         for (int i = 0; i < p.world; ++i) {
             p.mbox_peer[i] = (double*)h->peer_mbox[i];
@@ -392,25 +474,46 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
     p.trace = h->trace; p.trace_steps = h->trace_steps;
     CK(h, cudaMemsetAsync(h->bar, 0, 8 * sizeof(unsigned long long), st));
     CK(h, cudaMemsetAsync(h->gparams, 0, GPARAMS_BYTES, st));
-    CK(h, cudaMemsetAsync(h->status, 0xFF, sizeof(long long), st));
+    if (phase != 2) CK(h, cudaMemsetAsync(h->status, 0xFF, sizeof(long long), st));
+    // ---- which kernel ----
+    // the resident batch kernel: independent series / one small series, C in shared memory for the whole launch
+    bool use3 = h->batch_ok && !external && (h->cfg.kernel == 3 || (h->cfg.kernel == 0 && (h->S > 1 || h->ntiles <= 32)));
+    size_t dyn3 = h->dyn_smem3;
+    if (use3 && eval) {
+        dyn3 = batch_dyn(h->ntiles, h->R, h->esize, true);
+        LaunchShape sb;
+        if (dyn3 > (size_t)h->maxsmem ||
+            (h->batch_nw8 ? SHAPE_B8 : SHAPE_B4)[h->R](h->cfg.dtype, dyn3, &sb) != cudaSuccess || sb.max_ctas_per_sm < 1) {
+            cudaGetLastError();
+            if (h->cfg.kernel == 3) return fail(h, PSMF_E_NOMEM, "batch kernel: no shared memory left for the evaluation buffers");
+            use3 = false;
+        }
+    }
     // the TMA-staged kernel needs 16-byte aligned rows of Y / M (bulk copies)
     const size_t es = h->esize;
     bool aligned = h->cps2 > 0 && ((uintptr_t)io->Y % 16 == 0) && ((size_t)io->ldy * es % 16 == 0) &&
                    ((size_t)io->y_series_stride * es % 16 == 0);
     if (io->M) aligned = aligned && ((uintptr_t)io->M % 16 == 0) && (io->ldm % 16 == 0) && (io->m_series_stride % 16 == 0);
-    bool use2 = aligned && h->cfg.dynamics != PSMF_DYN_EXTERNAL &&
+    bool use2 = !use3 && aligned && !eval && !external && h->cfg.dynamics != PSMF_DYN_EXTERNAL &&
                 (h->cfg.kernel == 2 || (h->cfg.kernel == 0 && h->ntiles >= 2 * (V2_CWARPS + 1)));
     if (h->cfg.kernel == 2 && !use2)
-        return fail(h, PSMF_E_INVALID, "kernel=2 requested but Y/M are not 16-byte aligned (or dynamics is external)");
+        return fail(h, PSMF_E_INVALID, "kernel=2 requested but Y/M are not 16-byte aligned, dynamics is external, or fused "
+                                       "evaluation was requested (direct-load / batch kernels only)");
     if (p.world > 1) {
         // row sharding: the kernel is a collective decision (psmf_mailbox_connect) -- the two kernels exchange
         // different statistics vectors, so a rank must never pick one from local facts alone
+        if (eval) return fail(h, PSMF_E_INVALID, "fused evaluation is per GPU: not available with row sharding");
         if (h->agreed_kernel == 2 && !aligned)
             return fail(h, PSMF_E_INVALID, "the ranks agreed on the TMA-staged kernel but this rank's Y/M are not 16-byte aligned "
                                            "(pad ldy/ldm to a multiple of 16 bytes, or create every engine with kernel=1)");
         use2 = h->agreed_kernel == 2;
     }
-    if (use2) {
+    if (use3) {
+        p.cps = 1;
+        CK(h, LAUNCH_B[h->R](p, h->cfg.dtype, h->S, dyn3, st, h->batch_nw8));
+        h->last_kernel = 3;
+        h->last_dyn = dyn3;
+    } else if (use2) {
         p.cps = h->cps2;
         p.nslot = h->nslot;
         p.trace_cta = h->cps2;
@@ -424,13 +527,204 @@ extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64
         p.gparams = h->gparams;
         CK(h, LAUNCH_S[h->R](p, h->cfg.dtype, h->cps2 + 1, h->dyn_smem2, st, true));
         h->last_kernel = 2;
+        h->last_dyn = h->dyn_smem2;
     } else {
-        CK(h, LAUNCH[h->R](p, h->cfg.dtype, h->S * h->cps, h->dyn_smem, st, h->cooperative));
+        size_t dyn1 = h->dyn_smem;
+        if (eval) {
+            const int64_t tiles_per = (h->ntiles + h->cps - 1) / h->cps + 1;
+            dyn1 += (size_t)tiles_per * TILE * 17 + 16;
+            LaunchShape sh1;
+            if (SHAPE[h->R](h->cfg.dtype, dyn1, &sh1) != cudaSuccess || sh1.max_ctas_per_sm < 1 ||
+                (h->cooperative && h->cps > h->num_sms * sh1.max_ctas_per_sm)) {
+                cudaGetLastError();
+                return fail(h, PSMF_E_NOMEM, "no shared memory left for the evaluation buffers at this d / grid");
+            }
+        }
+        CK(h, LAUNCH[h->R](p, h->cfg.dtype, h->S * h->cps, dyn1, st, h->cooperative));
         h->last_kernel = 1;
+        h->last_dyn = dyn1;
     }
-    h->launches_last = 1;
+    if (eval) {
+        eval_part_finish<<<h->S, 32, 0, st>>>(h->eval_part, p.cps, io->eval_out);
+        CK(h, cudaGetLastError());
+    }
+    h->launches_last = eval ? 2 : 1;
     h->last_stream = st;
-    h->step_base += (unsigned long long)n_steps;
+    if (phase != 1) h->step_base += (unsigned long long)n_steps;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_run(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k0, void* stream) {
+    if (!h) return PSMF_E_INVALID;
+    return run_impl(h, io, n_steps, k0, stream, h->cfg.exchange == PSMF_XCHG_EXTERNAL ? 1 : 0);
+}
+
+extern "C" int psmf_run_finish(psmf_handle h, const psmf_io* io, int64_t k0, void* stream) {
+    if (!h) return PSMF_E_INVALID;
+    return run_impl(h, io, 1, k0, stream, 2);
+}
+
+extern "C" int psmf_stats_buffer(psmf_handle h, double** dev_ptr, int32_t* count) {
+    if (!h || !dev_ptr || !count) return PSMF_E_INVALID;
+    if (!h->stats_ext) return fail(h, PSMF_E_STATE, "engine was not created with PSMF_XCHG_EXTERNAL");
+    *dev_ptr = h->stats_ext;
+    *count = nstat(h->R);
+    return PSMF_OK;
+}
+
+extern "C" int psmf_set_linear_dynamics(psmf_handle h, const double* A, const double* c, void* stream) {
+    if (!h || !A) return PSMF_E_INVALID;
+    if (h->cfg.dynamics != PSMF_DYN_LINEAR) return fail(h, PSMF_E_STATE, "engine was not created with PSMF_DYN_LINEAR");
+    CK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(h, cudaMemcpyAsync(h->lin, A, (size_t)h->R * h->R * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (c) CK(h, cudaMemcpyAsync(h->lin + h->R * h->R, c, (size_t)h->R * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    h->lin_set = true;
+    h->lin_has_c = c != nullptr;
+    return PSMF_OK;
+}
+
+static int tool_scratch(psmf_engine* h, size_t bytes) {
+    if (h->tool_bytes >= bytes) return PSMF_OK;
+    cudaFree(h->tool_buf);
+    h->tool_buf = nullptr;
+    h->tool_bytes = 0;
+    CK(h, cudaMalloc(&h->tool_buf, bytes));
+    h->tool_bytes = bytes;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_predict(psmf_handle h, int64_t n_pred, int64_t k0, const double* Xpred_in, double* Xpred_out, void* Ypred_out,
+                            int64_t ldp, int64_t pred_series_stride, void* stream) {
+    if (!h) return PSMF_E_INVALID;
+    if (n_pred < 1) return fail(h, PSMF_E_INVALID, "n_pred must be >= 1");
+    if (Ypred_out && ldp < h->d) return fail(h, PSMF_E_INVALID, "ldp < d");
+    if (h->cfg.dynamics == PSMF_DYN_EXTERNAL && !Xpred_in)
+        return fail(h, PSMF_E_INVALID, "PSMF_DYN_EXTERNAL: the caller owns f, pass the rolled-out states in Xpred_in");
+    if (h->cfg.dynamics == PSMF_DYN_LINEAR && !h->lin_set && !Xpred_in)
+        return fail(h, PSMF_E_STATE, "PSMF_DYN_LINEAR: call psmf_set_linear_dynamics first");
+    CK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const double* Xp = Xpred_in;
+    if (!Xp) {
+        double* dst = Xpred_out;
+        if (!dst) {
+            int rc = tool_scratch(h, (size_t)h->S * n_pred * h->R * sizeof(double));
+            if (rc) return rc;
+            dst = h->tool_buf;
+        }
+        rollout_kernel<<<h->S, 32, 0, st>>>(h->state, h->R, h->cfg.dynamics, h->lin, h->lin_has_c ? h->lin + h->R * h->R : nullptr, k0,
+                                           n_pred, dst);
+        CK(h, cudaGetLastError());
+        Xp = dst;
+    } else if (Xpred_out && Xpred_out != Xpred_in) {
+        CK(h, cudaMemcpyAsync(Xpred_out, Xpred_in, (size_t)h->S * n_pred * h->R * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    if (Ypred_out) {
+        const int64_t groups = (h->ntiles + TOOL_WARPS - 1) / TOOL_WARPS;
+        dim3 grid((unsigned)(groups > 1024 ? 1024 : groups), (unsigned)h->S);
+        if (h->cfg.dtype == PSMF_F64)
+            project_kernel<double><<<grid, TOOL_WARPS * 32, 0, st>>>((const double*)h->C, h->ntiles * TILE * h->R, h->d, h->R, Xp, n_pred,
+                                                                    (double*)Ypred_out, ldp, pred_series_stride);
+        else
+            project_kernel<float><<<grid, TOOL_WARPS * 32, 0, st>>>((const float*)h->C, h->ntiles * TILE * h->R, h->d, h->R, Xp, n_pred,
+                                                                   (float*)Ypred_out, ldp, pred_series_stride);
+        CK(h, cudaGetLastError());
+    }
+    h->last_stream = st;
+    return PSMF_OK;
+}
+
+extern "C" int psmf_eval_full(psmf_handle h, const double* X, int64_t n_steps, const void* Yorig, int64_t ldy, int64_t y_series_stride,
+                              const uint8_t* E, int64_t lde, int64_t e_series_stride, double* out, void* stream) {
+    if (!h || !X || !Yorig || !E || !out) return PSMF_E_INVALID;
+    if (n_steps < 1 || ldy < h->d || lde < h->d) return fail(h, PSMF_E_INVALID, "bad n_steps / ldy / lde");
+    CK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t groups = (h->ntiles + TOOL_WARPS - 1) / TOOL_WARPS;
+    const int nparts = (int)(groups > 256 ? 256 : groups);
+    int rc = tool_scratch(h, (size_t)h->S * nparts * 2 * sizeof(double));
+    if (rc) return rc;
+    dim3 grid((unsigned)nparts, (unsigned)h->S);
+    if (h->cfg.dtype == PSMF_F64)
+        eval_full_kernel<double><<<grid, TOOL_WARPS * 32, 0, st>>>((const double*)h->C, h->ntiles * TILE * h->R, h->d, h->R, X, n_steps,
+                                                                  (const double*)Yorig, ldy, y_series_stride, E, lde, e_series_stride, h->tool_buf);
+    else
+        eval_full_kernel<float><<<grid, TOOL_WARPS * 32, 0, st>>>((const float*)h->C, h->ntiles * TILE * h->R, h->d, h->R, X, n_steps,
+                                                                 (const float*)Yorig, ldy, y_series_stride, E, lde, e_series_stride, h->tool_buf);
+    CK(h, cudaGetLastError());
+    eval_full_finish<<<h->S, 32, 0, st>>>(h->tool_buf, nparts, out);
+    CK(h, cudaGetLastError());
+    h->last_stream = st;
+    return PSMF_OK;
+}
+
+// ---- handle-free tools: ingest and the missing-segment generator ------------------------------------------------
+static int tool_fail(cudaError_t e, const char* what) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return PSMF_E_CUDA;
+}
+#define TCK(call)                                                     \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return tool_fail(e__, #call);         \
+    } while (0)
+
+extern "C" int psmf_ingest(int32_t device, const double* src, int64_t d, int64_t n, int32_t dtype, int32_t keep_nan, void* Y_out,
+                           int64_t ldy, uint8_t* M_out, int64_t ldm, void* stream) {
+    if (!src || d < 1 || n < 1 || (!Y_out && !M_out) || (Y_out && ldy < d) || (M_out && ldm < d) ||
+        (dtype != PSMF_F64 && dtype != PSMF_F32))
+        return fail(nullptr, PSMF_E_INVALID, "psmf_ingest: bad arguments");
+    TCK(cudaSetDevice(device));
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((d + 31) / 32)), block(32, 8);
+    if (grid.y > 65535) return fail(nullptr, PSMF_E_INVALID, "psmf_ingest: d too large for one call (split the rows)");
+    const int mode = keep_nan ? INGEST_KEEP_NAN : 0;
+    if (dtype == PSMF_F64)
+        ingest_kernel<double><<<grid, block, 0, (cudaStream_t)stream>>>(src, d, n, mode, (double*)Y_out, ldy, M_out, ldm);
+    else
+        ingest_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src, d, n, mode, (float*)Y_out, ldy, M_out, ldm);
+    TCK(cudaGetLastError());
+    return PSMF_OK;
+}
+
+extern "C" int psmf_transpose_mask(int32_t device, const uint8_t* src, int64_t d, int64_t n, uint8_t* dst, int64_t ld, void* stream) {
+    if (!src || !dst || d < 1 || n < 1 || ld < d) return fail(nullptr, PSMF_E_INVALID, "psmf_transpose_mask: bad arguments");
+    TCK(cudaSetDevice(device));
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((d + 31) / 32)), block(32, 8);
+    if (grid.y > 65535) return fail(nullptr, PSMF_E_INVALID, "psmf_transpose_mask: d too large for one call (split the rows)");
+    transpose_mask_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, d, n, dst, ld);
+    TCK(cudaGetLastError());
+    return PSMF_OK;
+}
+
+extern "C" int psmf_missing_segments(int32_t device, int32_t dtype, void* Y, int64_t ldy, uint8_t* E, int64_t lde, int64_t d, int64_t n,
+                                     const int64_t* starts, int32_t seg, uint64_t* count_dev, void* stream) {
+    if (!Y || !E || !starts || !count_dev || d < 1 || n < 1 || ldy < d || lde < d || seg < 1 || (dtype != PSMF_F64 && dtype != PSMF_F32))
+        return fail(nullptr, PSMF_E_INVALID, "psmf_missing_segments: bad arguments");
+    TCK(cudaSetDevice(device));
+    const unsigned blocks = (unsigned)((d + 255) / 256);
+    if (dtype == PSMF_F64)
+        missing_segments_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)Y, ldy, E, lde, d, n, starts, seg,
+                                                                                 (unsigned long long*)count_dev);
+    else
+        missing_segments_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)Y, ldy, E, lde, d, n, starts, seg,
+                                                                                (unsigned long long*)count_dev);
+    TCK(cudaGetLastError());
+    return PSMF_OK;
+}
+
+extern "C" int psmf_count_nan(int32_t device, int32_t dtype, const void* Y, int64_t ldy, int64_t d, int64_t n, uint64_t* count_dev,
+                              void* stream) {
+    if (!Y || !count_dev || d < 1 || n < 1 || ldy < d || (dtype != PSMF_F64 && dtype != PSMF_F32))
+        return fail(nullptr, PSMF_E_INVALID, "psmf_count_nan: bad arguments");
+    TCK(cudaSetDevice(device));
+    const int64_t total = d * n;
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
+    if (dtype == PSMF_F64)
+        count_nan_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double*)Y, ldy, d, n, (unsigned long long*)count_dev);
+    else
+        count_nan_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)Y, ldy, d, n, (unsigned long long*)count_dev);
+    TCK(cudaGetLastError());
     return PSMF_OK;
 }
 
@@ -461,10 +755,10 @@ extern "C" int psmf_status(psmf_handle h, int64_t* first_bad_step) {
 
 extern "C" int psmf_launch_info(psmf_handle h, int32_t* ctas, int32_t* threads, int32_t* smem_bytes, int32_t* launches) {
     if (!h) return PSMF_E_INVALID;
-    const bool k2 = h->last_kernel == 2;
-    if (ctas) *ctas = k2 ? h->cps2 + 1 : h->cps;
-    if (threads) *threads = k2 ? h->threads2 : h->threads;
-    if (smem_bytes) *smem_bytes = (int32_t)(k2 ? h->dyn_smem2 : h->dyn_smem);
+    const int k = h->last_kernel;
+    if (ctas) *ctas = k == 2 ? h->cps2 + 1 : (k == 3 ? 1 : h->cps);
+    if (threads) *threads = k == 2 ? h->threads2 : (k == 3 ? h->threads3 : h->threads);
+    if (smem_bytes) *smem_bytes = (int32_t)h->last_dyn;
     if (launches) *launches = h->launches_last;
     return PSMF_OK;
 }

@@ -20,8 +20,9 @@ constexpr int MAXR = 16;
 constexpr int MAX_PEERS = 8;
 
 // flags (mirror include/psmf_b200.h)
-constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16, F_LL_STUDENT = 32;
-constexpr int DYN_IDENTITY = 0, DYN_COS = 1, DYN_EXTERNAL = 3;
+constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16, F_LL_STUDENT = 32, F_NAN_MASK = 64;
+constexpr int DYN_IDENTITY = 0, DYN_COS = 1, DYN_LINEAR = 2, DYN_EXTERNAL = 3;
+constexpr int NEVAL = 4;     // fused evaluation record (include/psmf_b200.h PSMF_EVAL_*)
 // debug-only flag bits (env PSMF_DEBUG_FLAGS; results are WRONG with them): compiled in only with -DPSMF_DEBUG,
 // release builds of the library carry neither the flags nor the environment knobs
 #ifdef PSMF_DEBUG
@@ -36,6 +37,9 @@ constexpr int F_DBG_NOCOMPUTE = 1 << 20, F_DBG_NOSTORE = 1 << 21;
 __host__ __device__ constexpr int tile_pos(int j, int i) { return j * 32 + (i ^ ((j & 7) << 2)); }
 
 constexpr int V1_WARPS = 8;     // direct-load kernel: warps per CTA (one tile per warp at a time)
+constexpr int V3_PF = 4;        // resident batch kernel: tiles per warp whose y / m are prefetched one step ahead
+// resident batch kernel: CTAs per SM the register budget is sized for (shared memory permitting)
+__host__ __device__ constexpr int batch_min_ctas(int R, int NW) { return NW >= 8 ? 2 : (R <= 8 ? 5 : (R <= 12 ? 4 : 3)); }
 constexpr int V2_CWARPS = 14;   // TMA-staged kernel: pass warps (+1 reduce warp, +1 producer warp)
 constexpr int V2_TS = 4;        // TMA-staged kernel: tiles per shared-memory chunk slot
 constexpr int MAXW = 12;        // max warps that write per-warp partial statistics in any kernel
@@ -51,6 +55,14 @@ __host__ __device__ constexpr int nstat2_pad(int R) { return (nstat2(R) + 7) / 8
 __host__ __device__ constexpr int gram_off(int R, int j) { return j * R - j * (j - 1) / 2; }
 // tagged 16-byte cells behind KParams.gparams: [2][2 MAXR] parameter sets, then [2][nstat2_pad(MAXR)] reduced totals
 constexpr size_t GPARAMS_BYTES = (size_t)(4 * MAXR + 2 * nstat2_pad(MAXR)) * 16;
+
+// resident batch kernel: dynamic shared memory = [C tiles][residuals e (ntiles * 32 doubles)][evaluation buffers]
+__host__ __device__ constexpr size_t batch_c_bytes(int64_t ntiles, int R, size_t esize) {
+    return ((size_t)ntiles * R * TILE * esize + 127) / 128 * 128;
+}
+__host__ __device__ constexpr size_t batch_dyn_bytes(int64_t ntiles, int R, size_t esize, bool eval) {
+    return batch_c_bytes(ntiles, R, esize) + (size_t)ntiles * TILE * 8 + (eval ? (size_t)ntiles * TILE * 17 + 16 : 0);
+}
 
 // small-state layout (doubles per series)
 __host__ __device__ constexpr int st_x(int R) { return 0; }
@@ -93,6 +105,18 @@ struct KParams {
     double* gparams;          // pipelined kernel: [2][2 * MAXR] parameter sets published by the control CTA
     int32_t trace_steps;      // debug: number of steps recorded in `trace`
     unsigned long long* trace; // debug: [trace_steps][8] globaltimer stamps of CTA 0 (or nullptr)
+    // fused evaluation (common.py:79-94): both nullptr = off
+    const void* Yorig;        // original values, same layout / strides as Y
+    const uint8_t* E; int64_t lde; int64_t esst;   // 1 = evaluate here (the artificially removed entries, Mmiss)
+    double sig;               // interval half-width in sigmas (rPSMF.py:121-123)
+    double* eval_part;        // [n_series][cps][NEVAL] per-CTA sums of this launch: sum (yhat - yorig)^2, inside, count
+    // caller-driven statistics exchange (psmf_config.exchange = external): 0 = whole step, 1 = pass + reduction only
+    // (statistics -> stats_ext, residuals -> e_ext), 2 = r x r update + rank-1 update from stats_ext / e_ext
+    int32_t phase;
+    double* stats_ext;        // nstat_pad(R) doubles
+    double* e_ext;            // d doubles
+    const double* lin_A;      // DYN_LINEAR: (r, r) row-major A and (r) offset c (x_bar = A x + c, F = A), device pointers
+    const double* lin_c;
     unsigned long long spin_ns; // a wait (tagged cell, mbarrier, grid barrier, NVLink mailbox) that makes no progress for
                                 // this long gives up: status word <- STATUS_TIMEOUT | step, abort word (bar[7]) <- 1
 };
@@ -129,4 +153,7 @@ typedef cudaError_t (*shape_fn)(int dtype, size_t dyn_smem, LaunchShape*);
     cudaError_t shape_filter_r##n(int, size_t, LaunchShape*);                                               \
     cudaError_t launch_stream_r##n(const KParams&, int, int, size_t, cudaStream_t, bool);                   \
     cudaError_t shape_stream_r##n(int, size_t, LaunchShape*);                                               \
+    cudaError_t launch_batch_r##n(const KParams&, int, int, size_t, cudaStream_t, bool);                    \
+    cudaError_t shape_batch4_r##n(int, size_t, LaunchShape*);                                               \
+    cudaError_t shape_batch8_r##n(int, size_t, LaunchShape*);                                               \
     }

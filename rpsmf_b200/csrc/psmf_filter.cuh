@@ -304,6 +304,69 @@ __device__ __forceinline__ void acc_writeout(TileAcc<R>& A, double* __restrict__
         if (base + i < lim) red[ngram(R) + base + i] = A.v[i];
 }
 
+// x_bar_i = c_i + sum_k A_ik x_k in a FIXED operation order: the pipelined kernel evaluates it in two places (the
+// published x_bar of the data CTAs and the control CTA's own copy) and both must be bit-identical
+template <int R>
+__device__ __forceinline__ double linear_predict(const KParams& p, const double* __restrict__ x, int i) {
+    double acc = p.lin_c != nullptr ? p.lin_c[i] : 0.0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) acc = fma(p.lin_A[i * R + k], x[k], acc);
+    return acc;
+}
+
+// ---- fused evaluation (ExperimentImpute/common.py:79-94) -----------------------------------------------------
+// Accumulated inside the row pass instead of materialising (n, d) Yrec / YrecL / YrecH arrays: over the entries
+// marked in E (the artificially removed ones, Mmiss) the squared one-step prediction error (Epred, rPSMF.py:139) and
+// the number of original values inside the interval yhat -+ sig sqrt(U) (rPSMF.py:121-123, common.py:87-94).  U
+// needs eta of the SAME step, which only exists after the solve: the prediction, the original value and the flags of
+// a row wait in shared memory and are scored at the start of the next pass (or in the flush after the last step).
+struct EvalAcc {
+    double se = 0.0, ne = 0.0, inside = 0.0;
+};
+struct EvalBuf {          // per-CTA shared-memory buffers, one entry per local row (nullptr: evaluation off)
+    double* yh;           // prediction of the previous step
+    double* yo;           // original value of the previous step
+    unsigned char* fl;    // bit 0: evaluate, bit 1: observed (m_i)
+};
+__device__ __forceinline__ void eval_cover(EvalAcc& ev, const EvalBuf& eb, int rl, double a, double eta, double N, bool robust, double sig) {
+    const unsigned f = eb.fl[rl];
+    if (f & 1u) {
+        const double U = robust ? __dadd_rn(__dmul_rn(a, (double)((f >> 1) & 1u)), eta) : N;    // rPSMF.py:112 / PSMF.py:83-84
+        const double s = __dmul_rn(sig, sqrt(U));
+        const double yh = eb.yh[rl], yo = eb.yo[rl];
+        const double hi = __dadd_rn(yh, s), lo = __dsub_rn(yh, s);                              // rPSMF.py:122-123
+        ev.inside += (yo < hi && lo < yo) ? 1.0 : 0.0;                                          // common.py:91-93
+    }
+}
+__device__ __forceinline__ void eval_row(EvalAcc& ev, const EvalBuf& eb, int rl, bool ei, bool mi, double yh, double yo) {
+    if (ei) {
+        const double dlt = __dsub_rn(yh, yo);
+        ev.se = __dadd_rn(ev.se, __dmul_rn(dlt, dlt));                                          // common.py:79-84
+        ev.ne += 1.0;
+    }
+    eb.yh[rl] = yh;
+    eb.yo[rl] = yo;
+    eb.fl[rl] = (unsigned char)((ei ? 1u : 0u) | (mi ? 2u : 0u));
+}
+// end of launch: per-lane sums -> warp (butterfly, fixed order) -> shared scratch -> CTA record in p.eval_part
+template <int NW>
+__device__ __forceinline__ void eval_writeout(const KParams& p, EvalAcc& ev, double* scratch /* NW * 4 doubles */, int series, int part,
+                                              int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const double a = warp_allsum(ev.se), b = warp_allsum(ev.inside), c = warp_allsum(ev.ne);
+    if (lane == 0) {
+        scratch[warp * 4 + 0] = a;
+        scratch[warp * 4 + 1] = b;
+        scratch[warp * 4 + 2] = c;
+    }
+    __syncthreads();
+    if (tid < 3) {
+        double t = 0.0;
+        for (int w = 0; w < NW; ++w) t += scratch[w * 4 + tid];
+        p.eval_part[((int64_t)series * p.cps + part) * NEVAL + tid] = t;
+    }
+}
+
 // ---- predict half: x_bar = f(x), P_bar = F P F' + Q, V x_bar, a (all `nthr` threads; ends with a barrier) ----
 template <int R, int BAR = 0>
 __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, int series, int nthr) {
@@ -317,6 +380,8 @@ __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, i
             fd = -sin(arg);
         } else if (p.dynamics == DYN_EXTERNAL) {
             xb = p.xbar_ext[(int64_t)series * R + tid];
+        } else if (p.dynamics == DYN_LINEAR) {                                // x_bar = A x + c (psmf.py:104 with a linear f;
+            xb = linear_predict<R>(p, sh.x, tid);                             //  ExperimentChange/PSMF.m:29: Xp = A * X)
         } else {
             xb = sh.x[tid];                                                   // rPSMF.py:86
         }
@@ -351,8 +416,8 @@ __device__ void predict_cta(const KParams& p, Smem<R>& sh, int tid, int64_t k, i
         double pb;
         if (simp) {                                                           // synthetic_psmf.py:83-84
             pb = sh.P[idx];
-        } else if (p.dynamics == DYN_EXTERNAL) {                              // psmf.py:115 with a dense F
-            const double* F = p.F_ext + (int64_t)series * R * R;
+        } else if (p.dynamics == DYN_EXTERNAL || p.dynamics == DYN_LINEAR) {   // psmf.py:115 with a dense F (PSMF.m:30: A P A' + Q)
+            const double* F = p.dynamics == DYN_LINEAR ? p.lin_A : p.F_ext + (int64_t)series * R * R;
             double acc = 0.0;
             for (int k2 = 0; k2 < R; ++k2) {
                 double t2 = 0.0;
@@ -520,6 +585,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         if (lane == 0) {
             sh.sc[0] = omega; sh.sc[1] = eta; sh.sc[2] = N; sh.sc[3] = phi; sh.sc[4] = sSe;
             sh.sc[5] = p.alpha * phi; sh.sc[6] = p.beta * omega;
+            sh.sc[7] = a;                                  // a of THIS step (sh.a is overwritten by the next predict)
             if (writer) {
                 if (p.scal_out != nullptr) {
                     double* so = p.scal_out + ((int64_t)series * p.n_steps + t) * NSCAL;
@@ -658,8 +724,26 @@ __device__ __forceinline__ void grid_reduce(const KParams& p, double* __restrict
     if (p.world > 1) gpu_exchange<NST, NSP, BAR>(p, tot, part_v, tid, t, part, nthr, 1);
 }
 
+// ---- observation of one row: value and mask, whatever the encoding --------------------------------------
+// bytes: y zero-filled where missing + one mask byte (rPSMF.py:198-202); F_NAN_MASK: missing entries are NaN in y (the
+// raw data form, rPSMF.py:160-164) and there is no mask stream: m = !isnan(y), y := 0 where missing.
+template <typename T>
+__device__ __forceinline__ void observe(const KParams& p, const T* __restrict__ Yt, const uint8_t* __restrict__ Mt, int64_t row, bool inb,
+                                        double& yi, bool& mi) {
+    yi = inb ? (double)Yt[row] : 0.0;
+    mi = inb;
+    if (Mt != nullptr) {
+        if (inb) mi = Mt[row] != 0;
+    } else if ((p.flags & F_NAN_MASK) != 0) {
+        mi = inb && !isnan(yi);
+        yi = mi ? yi : 0.0;
+    }
+}
+
 // ---- direct-load persistent kernel: C tiles are read from / written to global memory by the warp that
 // owns them; general fallback (any alignment, any d) and the path for small problems / batched series ----
+// p.phase (caller-driven statistics exchange, one step per launch): 1 = pass + grid reduction, statistics -> p.stats_ext
+// and residuals -> p.e_ext; 2 = r x r update from p.stats_ext (all-reduced by the caller) + the rank-1 update of C.
 template <int R, typename T>
 __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KParams p) {
     constexpr int NW = V1_WARPS, NSP = nstat_pad(R), NST = nstat(R);
@@ -677,6 +761,14 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
     const int te = (int)((int64_t)ntiles * (part + 1) / p.cps);
     const bool writer = part == 0;
     double* stage = stage_all + warp * R * TILE;
+    const int nrows = (te - tb) * TILE;
+    const bool evalon = p.E != nullptr;
+    EvalBuf eb;                                                                // behind the residual buffer (host sizes it)
+    eb.yh = ebuf + ((int64_t)ntiles + p.cps - 1) / p.cps * TILE + TILE;
+    eb.yo = eb.yh + nrows;
+    eb.fl = reinterpret_cast<unsigned char*>(eb.yo + nrows);
+    EvalAcc ev;
+    const bool robust = (p.flags & F_ROBUST) != 0;
 
     T* Cs = reinterpret_cast<T*>(p.C) + (int64_t)series * p.c_series_stride;
     double* stg = p.state + (int64_t)series * st_size(R);
@@ -696,7 +788,9 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
         sh.rho = stg[st_rho(R)];
         sh.lam = stg[st_lam(R)];
     }
-    for (int i = tid; i < (te - tb) * TILE; i += blockDim.x) ebuf[i] = 0.0;
+    for (int i = tid; i < nrows; i += blockDim.x) ebuf[i] = p.phase == 2 ? p.e_ext[(int64_t)tb * TILE + i] : 0.0;
+    if (evalon)
+        for (int i = tid; i < nrows; i += blockDim.x) eb.fl[i] = 0;
     __syncthreads();
     predict_cta<R>(p, sh, tid, p.k0, series, blockDim.x);
 
@@ -704,48 +798,65 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
         const T* __restrict__ Yt = reinterpret_cast<const T*>(p.Y) + (int64_t)series * p.ysst + t * p.ldy;
         const uint8_t* __restrict__ Mt = p.M ? p.M + (int64_t)series * p.msst + t * p.ldm : nullptr;
         T* Yrec_t = p.Yrec ? reinterpret_cast<T*>(p.Yrec) + (int64_t)series * p.recsst + t * p.ldrec : nullptr;
+        const T* __restrict__ Yo_t = evalon ? reinterpret_cast<const T*>(p.Yorig) + (int64_t)series * p.ysst + t * p.ldy : nullptr;
+        const uint8_t* __restrict__ Et = evalon ? p.E + (int64_t)series * p.esst + t * p.lde : nullptr;
         stamp(p, t, 0);
         const double w1 = sh.w1, w0 = sh.w0;
-        TileAcc<R> acc;
-        acc.zero();
-        for (int tile = tb + warp; tile < te; tile += NW) {
-            const int64_t row = (int64_t)tile * TILE + lane;
-            const int rl = (tile - tb) * TILE + lane;
-            T* gt = Cs + (int64_t)tile * (R * TILE);
-            double c[R];
+        if (p.phase != 2) {
+            TileAcc<R> acc;
+            acc.zero();
+            for (int tile = tb + warp; tile < te; tile += NW) {
+                const int64_t row = (int64_t)tile * TILE + lane;
+                const int rl = (tile - tb) * TILE + lane;
+                T* gt = Cs + (int64_t)tile * (R * TILE);
+                double c[R];
 #pragma unroll
-            for (int j = 0; j < R; ++j) c[j] = (double)gt[tile_pos(j, lane)];
-            const double ep = ebuf[rl];
-            const bool inb = row < p.d;
-            bool mi = inb;
-            if (Mt != nullptr && inb) mi = Mt[row] != 0;
-            const double yi = inb ? (double)Yt[row] : 0.0;
-            double e, yh;
-            row_stats<R>(acc, sh, c, ep, inb, mi, yi, w1, w0, e, yh);
+                for (int j = 0; j < R; ++j) c[j] = (double)gt[tile_pos(j, lane)];
+                const double ep = ebuf[rl];
+                const bool inb = row < p.d;
+                bool mi;
+                double yi;
+                observe<T>(p, Yt, Mt, row, inb, yi, mi);
+                if (evalon && t > 0) eval_cover(ev, eb, rl, sh.sc[7], sh.sc[1], sh.sc[2], robust, p.sig);   // step t-1, now that eta exists
+                double e, yh;
+                row_stats<R>(acc, sh, c, ep, inb, mi, yi, w1, w0, e, yh);
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
-                gt[tile_pos(j, lane)] = (T)c[j];
-                stage[tile_pos(j, lane)] = c[j];
+                for (int j = 0; j < R; ++j) {
+                    gt[tile_pos(j, lane)] = (T)c[j];
+                    stage[tile_pos(j, lane)] = c[j];
+                }
+                ebuf[rl] = e;
+                if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
+                if (evalon) eval_row(ev, eb, rl, inb && Et[row] != 0, mi, yh, inb ? (double)Yo_t[row] : 0.0);
+                const unsigned mbits = __ballot_sync(FULL, mi);
+                __syncwarp();
+                tile_gram<R, double>(acc, stage, mbits, lane);
+                __syncwarp();
             }
-            ebuf[rl] = e;
-            if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
-            const unsigned mbits = __ballot_sync(FULL, mi);
-            __syncwarp();
-            tile_gram<R, double>(acc, stage, mbits, lane);
-            __syncwarp();
-        }
-        acc_writeout<R>(acc, red + warp * NSP, w1, lane);
-        stamp(p, t, 1);
-        __syncthreads();
-        stamp(p, t, 2);
-        if (tid < NST) {                                   // CTA partial: fixed order over the warps
-            double s = 0.0;
+            acc_writeout<R>(acc, red + warp * NSP, w1, lane);
+            stamp(p, t, 1);
+            __syncthreads();
+            stamp(p, t, 2);
+            if (tid < NST) {                                   // CTA partial: fixed order over the warps
+                double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) s += red[w * NSP + tid];
-            sh.part[tid] = s;
+                for (int w = 0; w < NW; ++w) s += red[w * NSP + tid];
+                sh.part[tid] = s;
+            }
+            grid_reduce<NST, NSP>(p, sh.part, sh.tot, tid, lane, warp, t, series, part, blockDim.x);
+            stamp(p, t, 5);
         }
-        grid_reduce<NST, NSP>(p, sh.part, sh.tot, tid, lane, warp, t, series, part, blockDim.x);
-        stamp(p, t, 5);
+        if (p.phase == 1) {
+            // statistics of this GPU's rows -> the caller's collective; residuals survive the launch in global memory
+            if (writer)
+                for (int e = tid; e < NST; e += blockDim.x) p.stats_ext[e] = sh.tot[e];
+            for (int i = tid; i < nrows; i += blockDim.x) p.e_ext[(int64_t)tb * TILE + i] = ebuf[i];
+            return;
+        }
+        if (p.phase == 2) {
+            for (int e = tid; e < NST; e += blockDim.x) sh.tot[e] = p.stats_ext[e];
+            __syncthreads();
+        }
         small_update<R, GJ_THREADS>(p, sh, tid, lane, warp, series, t, writer, blockDim.x);
         stamp(p, t, 6);
     }
@@ -757,6 +868,11 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
         const double ep = ebuf[rl];
 #pragma unroll
         for (int j = 0; j < R; ++j) gt[tile_pos(j, lane)] = (T)fma(ep, sh.g[j], (double)gt[tile_pos(j, lane)]);
+        if (evalon) eval_cover(ev, eb, rl, sh.sc[7], sh.sc[1], sh.sc[2], robust, p.sig);   // the last step of the launch
+    }
+    if (evalon) {
+        __syncthreads();
+        eval_writeout<NW>(p, ev, red, series, part, tid);
     }
     if (writer) {
         for (int i = tid; i < R * R; i += blockDim.x) {

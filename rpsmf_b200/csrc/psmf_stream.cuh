@@ -228,6 +228,13 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
         }
 #endif
         // ---- phase 1, lane = row ----
+        // observation of steps p-1 and p: mask byte, or NaN-encoded missing entries (PSMF_NAN_MASK)
+        double ypv = (double)ym.yp, ycv = (double)ym.yc;
+        bool mpo = ym.mp != 0, mco = ym.mc != 0;
+        if ((p.flags & F_NAN_MASK) != 0) {
+            mpo = !isnan(ypv); mco = !isnan(ycv);
+            ypv = mpo ? ypv : 0.0; ycv = mco ? ycv : 0.0;
+        }
         double c[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) c[j] = (double)tile[tile_pos(j, lane)];
@@ -242,7 +249,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
 #pragma unroll
             for (int j = 0; j < R; ++j) yh4[j & 3] = fma(c[j], xbp[j], yh4[j & 3]);     // rPSMF.py:89
             const double yh = (yh4[0] + yh4[1]) + (yh4[2] + yh4[3]);
-            e = (double)ym.yp - ((inb && ym.mp != 0) ? yh : 0.0);  // rPSMF.py:101
+            e = ypv - ((inb && mpo) ? yh : 0.0);                   // rPSMF.py:101
             if (Yrec_prev != nullptr && inb) Yrec_prev[row] = (T)yh;
         }
         if constexpr (FLUSH) {                                     // C_n = C_{n-1} + e_{n-1} g_{n-1}'
@@ -254,8 +261,8 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
 #pragma unroll
             for (int j = 0; j < R; ++j) tile[tile_pos(j, lane)] = (T)c[j];
             ebuf[rl] = e;
-            const bool mi = inb && ym.mc != 0;
-            const double yi = (double)ym.yc;
+            const bool mi = inb && mco;
+            const double yi = ycv;
             acc.v[0] += mi ? e * e : 0.0;                          // kappa
             acc.v[1] += mi ? yi * e : 0.0;                         // psi
             acc.v[2] += mi ? yi * yi : 0.0;                        // gamma
@@ -709,12 +716,23 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
             }
             kbj += __shfl_xor_sync(FULL, kbj, 16);
             double xn = 0.0, xnext = 0.0;
+            if (lane < R) xn = sh.xb[lane] + kbj;                              // rPSMF.py:104 (simplified: x = x_bar)
+            if (p.dynamics == DYN_LINEAR) {
+                // x_bar_{t+1} = A x_t + c in the operation order of linear_predict (predict_cta recomputes it from sh.x
+                // and must get the same bits: the data CTAs see this copy, the control CTA its own)
+                double acc = (lane < R && p.lin_c != nullptr) ? p.lin_c[lane] : 0.0;
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const double xk = __shfl_sync(FULL, xn, k);
+                    if (lane < R) acc = fma(p.lin_A[lane * R + k], xk, acc);
+                }
+                xnext = acc;
+            }
             if (lane < R) {
-                xn = sh.xb[lane] + kbj;                                        // rPSMF.py:104 (simplified: x = x_bar)
                 if (p.dynamics == DYN_COS) {
                     const double arg = __dadd_rn(__dmul_rn(__dmul_rn(6.283185307179586, sh.th[lane]), (double)(p.k0 + t + 1)), xn);
                     xnext = cos(arg);
-                } else {
+                } else if (p.dynamics != DYN_LINEAR) {
                     xnext = xn;                        // external dynamics run one step per launch: set n is never used
                 }
                 cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + lane, sh.g[lane], tag_of((unsigned long long)t + 2ULL));

@@ -41,6 +41,29 @@ def prepare_missing(Ymiss, missRatio, misSeg=20):
     return ratio, Mmiss
 
 
+def prepare_missing_device(Yorig, missRatio, misSeg=20, dtype=None, device=None):
+    """``prepare_missing`` with the data on the GPU: ``Yorig`` (d, n) with NaN = missing is
+    ingested once (transpose to time-major on the device, NaN kept); per sweep the host draws the d segment starts from
+    the SAME random stream as the reference (one ``randint(1, n - misSeg)`` per row, in row order -- a vectorised draw
+    consumes the legacy generator identically) and the device removes the segments and counts.  Returns
+    ``(Y_tm, E_tm, ratio)``: time-major NaN-encoded observations (feed them to an engine created with ``nan_mask=True``),
+    the uint8 mask of artificially removed entries (``Mmiss`` transposed) and the achieved ratio -- bit-identical to the
+    reference's ``(Ymiss, Mmiss, ratio)``; only d integers per sweep cross PCIe."""
+    import torch
+    from .engine import count_nan, ingest, missing_segments
+    Y_tm, _ = ingest(Yorig, dtype=dtype or torch.float64, keep_nan=True, want_mask=False, device=device)
+    n, d = Y_tm.shape
+    E_tm = torch.zeros((n, d), dtype=torch.uint8, device=Y_tm.device)
+    n_default = count_nan(Y_tm)
+    removed = 0
+    ratio = n_default / (d * n)
+    while ratio < missRatio:
+        starts = np.random.randint(1, n - misSeg, size=d)          # == d scalar draws in row order (common.py:70)
+        removed += missing_segments(Y_tm, E_tm, starts, misSeg)
+        ratio = (n_default + float(removed)) / (d * n)
+    return Y_tm, E_tm, ratio
+
+
 def matrix_hash(A):
     """blake2b-128 of the raw bytes (common.py:108-111): the ``hashes`` of the published result files."""
     h = hashlib.blake2b(digest_size=16)

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from .engine import FilterEngine
+from .engine import FilterEngine, ingest, transpose_mask
 
 
 def _uniform_diag(R, d, name):
@@ -36,12 +36,6 @@ def _uniform_diag(R, d, name):
     return float(dg[0])
 
 
-def RMSEM(Y1, Y2, M):
-    """common.py:79-84 on device tensors."""
-    n = M.sum()
-    return torch.sqrt((((Y1 - Y2) * M) ** 2).sum() / n)
-
-
 def _fit(Y, C, X, d, n, r, M, Mmiss, V, Q0, R0, P, lambda0, sig, Iter, YorigInt, Einit, robust, device=None,
          dtype=torch.float64, return_details=False):
     Y = np.asarray(Y); M = np.asarray(M)
@@ -51,56 +45,49 @@ def _fit(Y, C, X, d, n, r, M, Mmiss, V, Q0, R0, P, lambda0, sig, Iter, YorigInt,
         raise ValueError("C must be (d, r) and X (r, n)")
     rho0 = _uniform_diag(R0, d, "R")
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-    f64 = torch.float64
 
     Epred = np.zeros([1, Iter + 1]); Efull = np.zeros([1, Iter + 1])
     Epred[:, 0] = Einit; Efull[:, 0] = Einit
     RunTime = np.zeros([1, Iter + 1])
     t0 = time.time()
 
-    # time-major device copies: y_t and m_t contiguous (the reference gathers a strided column per step)
-    Yt = torch.as_tensor(np.ascontiguousarray(Y.T), dtype=dtype).to(dev)
-    Mt = torch.as_tensor(np.ascontiguousarray(M.T != 0).astype(np.uint8)).to(dev)
-    Yo = torch.as_tensor(np.ascontiguousarray(np.asarray(YorigInt).T), dtype=f64).to(dev)
-    Mm = torch.as_tensor(np.ascontiguousarray(np.asarray(Mmiss).T), dtype=f64).to(dev)
+    # ingest on the device: (d, n) -> time-major (n, d), so that y_t / m_t are contiguous (the reference gathers a strided
+    # column per step); M and Mmiss travel as one byte per entry
+    Yt, _ = ingest(Y, dtype=dtype, keep_nan=False, want_mask=False, device=dev.index)
+    Mt = transpose_mask(M, device=dev.index)
+    Yo, _ = ingest(YorigInt, dtype=dtype, keep_nan=False, want_mask=False, device=dev.index)
+    Et = transpose_mask(Mmiss, device=dev.index)
 
     eng = FilterEngine(d, r, dtype=dtype, robust=robust, c_update_transpose=robust, dynamics=_capi.DYN_IDENTITY,
                        device=dev.index)
+    InsideBars = 0.0                                                            # Iter = 0: the bounds stay zero
+    details = {}
     try:
         eng.set_state(C_=C, V=V, P=P, x=np.ascontiguousarray(X[:, n - 1]), Q=Q0, rho=[rho0], lam=[lambda0 if robust else 0.0])
-        out = None
         for i in range(Iter):
             if robust:
                 eng.set_state(Q=Q0, rho=[rho0], lam=[lambda0])                 # rPSMF.py:77-79
-            # x_bar of t = 0 wraps to X[:, n-1] (rPSMF.py:86): that is the engine's carried x
-            out = eng.run(Yt, Mt, k0=1, want_X=True, want_Yrec=True, want_scal=True)
+            # x_bar of t = 0 wraps to X[:, n-1] (rPSMF.py:86): that is the engine's carried x.  The evaluation of the
+            # one-step predictions (Epred, the 2-sigma coverage) is accumulated inside the filter pass.
+            out = eng.run(Yt, Mt, k0=1, want_X=True, want_scal=return_details, want_Yrec=return_details, Yorig=Yo, E=Et, sig=sig)
             bad = eng.status()
-            Xd = out["X"]                                                       # (n, r)
-            X[:, :] = Xd.T.cpu().numpy()                                        # rPSMF.py:104 (in place)
-            Cd = eng.get_state()["C"].to(f64)
-            Yrec = out["Yrec"].to(f64)                                          # (n, d)
-            Yrec2 = Xd @ Cd.T                                                   # (C @ X).T, rPSMF.py:137
-            Epred[:, i + 1] = float(RMSEM(Yrec, Yo, Mm))
-            Efull[:, i + 1] = float(RMSEM(Yrec2, Yo, Mm))
+            ev = out["eval"].cpu().numpy().reshape(-1)
+            ef = eng.eval_full(out["X"], Yo, Et).cpu().numpy().reshape(-1)      # (C X - Yorig)^2 over Mmiss, final C (rPSMF.py:137)
+            X[:, :] = out["X"].cpu().numpy().T                                  # rPSMF.py:104 (in place)
+            Epred[:, i + 1] = np.sqrt(ev[_capi.EVAL_SSE] / ev[_capi.EVAL_COUNT])   # common.py:79-84
+            Efull[:, i + 1] = np.sqrt(ef[0] / ef[1])
+            InsideBars = float(ev[_capi.EVAL_INSIDE] / ev[_capi.EVAL_COUNT])    # common.py:87-94 (bounds of the last sweep)
             if bad >= 0:
                 Epred[:, i + 1] = np.nan; Efull[:, i + 1] = np.nan
             RunTime[:, i + 1] = time.time() - t0
-        if out is None:                                                         # Iter = 0: nothing was filtered
-            return (Epred, Efull, RunTime, 0.0, {}) if return_details else (Epred, Efull, RunTime, 0.0)   # bounds are all zero
-        sc = out["scal"]
-        if robust:
-            U = sc[:, _capi.SCAL_NAMES.index("a")].unsqueeze(1) * Mt.to(f64) + sc[:, _capi.SCAL_NAMES.index("eta")].unsqueeze(1)
-        else:
-            U = sc[:, _capi.SCAL_NAMES.index("N")].unsqueeze(1).expand(n, d)
-        sq = sig * torch.sqrt(U)                                                # rPSMF.py:121-123 / PSMF.py:83-84
-        lo, hi = Yrec - sq, Yrec + sq
-        inside = ((Mm == 1) & (Yo < hi) & (lo < Yo)).sum().to(f64) / Mm.sum()   # common.py:87-94
-        InsideBars = float(inside)
-        if return_details:
-            return Epred, Efull, RunTime, InsideBars, dict(C=Cd.cpu().numpy(), Yrec=Yrec.T.cpu().numpy(),
-                                                          scal=sc.cpu().numpy(), state=eng.get_state())
+            if return_details:
+                st = eng.get_state()
+                details = dict(C=st["C"].to(torch.float64).cpu().numpy(), Yrec=out["Yrec"].to(torch.float64).cpu().numpy().T,
+                               scal=out["scal"].cpu().numpy(), state=st, launch=eng.launch_info())
     finally:
         eng.close()
+    if return_details:
+        return Epred, Efull, RunTime, InsideBars, details
     return Epred, Efull, RunTime, InsideBars
 
 

@@ -238,14 +238,31 @@ class PSMFIter:
         self._predict_with(self._theta[i - 1], T, n_pred)
 
     def _predict_with(self, theta, T, n_pred):
+        """psmf.py:182-188 on the device: an r-dim roll-out of mu through f (one warp) and ONE d x r . r x n_pred product
+        with the filtered dictionary -- no per-horizon-step GEMV, nothing but the (n_pred, d) result crosses PCIe."""
         self._mu_pred = {T: self._mu[T]}
-        for k in range(T + 1, T + n_pred + 1):
-            self._mu_pred[k] = np.asarray(self.nonlinearity(theta, self._mu_pred[k - 1], k)).reshape(self._r, 1)
-        if n_pred > 0:                                        # one d x r . r x n_pred product (psmf.py:182-188)
-            Xp = np.concatenate([self._mu_pred[k] for k in range(T + 1, T + n_pred + 1)], axis=1)
-            Yp = self._C[T] @ Xp
-            for j, k in enumerate(range(T + 1, T + n_pred + 1)):
-                self._y_pred[k] = Yp[:, [j]]
+        if n_pred <= 0:
+            return
+        eng = self._get_engine()
+        if not getattr(self, "_state_on_device", False):
+            Q, rho = self._q_rho()
+            eng.set_state(C_=np.asarray(self._C[T], dtype=np.float64), V=self._V[T], P=self._P[T],
+                          x=np.asarray(self._mu[T], dtype=np.float64).reshape(-1), Q=Q, rho=[rho], lam=[self._lambda_entering(T)])
+        if self._dyn == _capi.DYN_EXTERNAL:
+            # the callable lives on the host: roll mu out here (r values per step), project on the device
+            mus, mu = [], self._mu[T]
+            for k in range(T + 1, T + n_pred + 1):
+                mu = np.asarray(self.nonlinearity(theta, mu, k), dtype=np.float64).reshape(self._r, 1)
+                mus.append(mu.reshape(-1))
+            Xo, Yp = eng.predict(n_pred, T + 1, Xpred=np.stack(mus))
+        else:
+            eng.set_state(theta=self._theta_vec(theta))
+            Xo, Yp = eng.predict(n_pred, T + 1)
+        Xh = Xo.cpu().numpy()
+        Yh = Yp.to(torch.float64).cpu().numpy()
+        for j, k in enumerate(range(T + 1, T + n_pred + 1)):
+            self._mu_pred[k] = Xh[j].reshape(self._r, 1)
+            self._y_pred[k] = Yh[j].reshape(self._d, 1)
 
     # ---- optimisers (psmf.py:190-248) ------------------------------------------------------------------
     def adam_init(self, gam=1e-3, b1=0.9, b2=0.999):

@@ -10,7 +10,7 @@ of any host-driven design, next to the in-kernel NVLink mailbox of the product p
 import os, sys
 import torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench
+import bench_data as bench
 from rpsmf_b200 import FilterEngine, shard_rows
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
@@ -19,7 +19,7 @@ dist.init_process_group("nccl", device_id=dev)
 d = int(os.environ.get("ROWS_PER_GPU", "125024")) * world
 r, T = 16, 400
 b, e = shard_rows(d, world, rank)
-Y, M, C0, x0 = bench.make_device_data(torch, dev, e - b, b, d, r, T, torch.float64)
+Y, M, C0, x0 = bench.make_series(torch, dev, e - b, b, d, r, T, torch.float64)
 init = bench.init_state(r)
 
 def timed(fn, n):

@@ -1,11 +1,11 @@
 import sys, numpy as np, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
-import bench
+import bench_data as bench
 from rpsmf_b200 import FilterEngine
 d, r, T = int(sys.argv[1]), 16, 160
 kernel = int(sys.argv[2]); ctas = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dev = torch.device("cuda", 0)
-Y, M, C0, x0 = bench.make_device_data(torch, dev, d, 0, d, r, T, torch.float64)
+Y, M, C0, x0 = bench.make_series(torch, dev, d, 0, d, r, T, torch.float64)
 init = bench.init_state(r)
 eng = FilterEngine(d, r, robust=True, kernel=kernel, ctas=ctas)
 eng.set_state(C_=C0, V=init["V"], P=init["P"], x=x0, Q=init["Q"], rho=[init["rho"]], lam=[init["lam"]])

@@ -238,10 +238,99 @@ def make_recursive():
     print("wrote pypsmf_recursive", os.path.getsize(os.path.join(HERE, "pypsmf_recursive.npz")) // 1024, "KiB")
 
 
+def make_linear():
+    """Linear dynamics x_bar = A x + c through the reference classes (psmf.py:104-115 with a linear callable; the
+    state-space form of ExperimentChange/PSMF.m:29-30 with H = I), full step + predict, PSMF and rPSMF."""
+    psmf = ref_loader.pypsmf()
+    out = {}
+    d, r, T, n_pred = 24, 5, 90, 8
+    rng = np.random.RandomState(77)
+    A = 0.95 * np.eye(r) + 0.05 * rng.randn(r, r)
+    c = 0.02 * rng.randn(r, 1)
+
+    def lin(theta, x, t):
+        return A @ x + c
+
+    Ct = rng.randn(d, r)
+    x = rng.randn(r, 1)
+    Y = np.zeros((T, d))
+    for t in range(T):
+        x = A @ x + c + 0.1 * rng.randn(r, 1)
+        Y[t] = (Ct @ x).reshape(d) + 0.3 * rng.standard_t(3, d)
+    y = {k + 1: Y[k].reshape(d, 1) for k in range(T)}
+    C0 = 0.1 * rng.randn(d, r)
+    V0 = 0.2 * np.eye(r); mu0 = 0.1 * np.ones((r, 1)); P0 = 0.5 * np.eye(r); Q = 0.02 * np.eye(r); rho = 0.5
+    th = np.zeros((1, 1))
+    for tag, robust in (("lin_psmf", False), ("lin_rpsmf", True)):
+        if robust:
+            o = psmf.rPSMFIter(th, C0, V0, mu0, P0, Q, rho * np.eye(d), 1.8, lin)
+        else:
+            o = psmf.PSMFIter(th, C0, V0, mu0, P0, {k: Q for k in range(T + 1)}, {k: rho * np.eye(d) for k in range(T + 1)}, lin)
+        o.step(y, 1, T)
+        o.predict(1, T, n_pred)
+        res = _collect(o, T, d)
+        ypp = np.stack([np.asarray(o._y_pred[k]).reshape(d) for k in range(T + 1, T + n_pred + 1)])
+        mupp = np.stack([np.asarray(o._mu_pred[k]).reshape(r) for k in range(T + 1, T + n_pred + 1)])
+        out.update({tag + "_" + k: v for k, v in dict(Y=Y, C0=C0, V0=V0, mu0=mu0.reshape(-1), P0=P0, Q=Q, rho=rho, A=A, c=c.reshape(-1),
+                                                      lam0=1.8, ypred_future=ypp, mu_future=mupp, **res).items()})
+    np.savez_compressed(os.path.join(HERE, "pypsmf_linear.npz"), **out)
+    print("wrote pypsmf_linear", os.path.getsize(os.path.join(HERE, "pypsmf_linear.npz")) // 1024, "KiB")
+
+
+def make_diagR():
+    """Diagonal, NON-uniform R (psmf.py:144-152 takes the Woodbury branch for any diagonal R; the flat functions accept
+    any (d, d) R): the class surface (cos dynamics, full step) and the two masked flat functions on a PM25 head."""
+    psmf = ref_loader.pypsmf()
+    data = ref_loader.synthetic_module("data")
+    out = {}
+    d, r, T = 20, 6, 100
+    np.random.seed(4242)
+    dat = data.generate_t_data(_cosnl, d=d, T=T, n_pred=0, r=r, var=0.1)
+    y = dat["y_train"]
+    Ymat = np.stack([y[k].reshape(d) for k in range(1, T + 1)])
+    C0 = 0.1 * np.random.randn(d, r)
+    theta0 = 0.1 * np.random.rand(r, 1)
+    rho_vec = 0.5 + 1.5 * np.random.rand(d)
+    V0 = 0.1 * np.eye(r); mu0 = 0.3 * np.ones((r, 1)); P0 = 0.5 * np.eye(r); Q = 0.01 * np.eye(r)
+    for tag, robust in (("diag_psmf", False), ("diag_rpsmf", True)):
+        if robust:
+            o = psmf.rPSMFIter(theta0, C0, V0, mu0, P0, Q, np.diag(rho_vec), 1.8, _cosnl)
+        else:
+            o = psmf.PSMFIter(theta0, C0, V0, mu0, P0, {k: Q for k in range(T + 1)}, {k: np.diag(rho_vec) for k in range(T + 1)}, _cosnl)
+        o.step(y, 1, T)
+        res = _collect(o, T, d)
+        if robust:
+            res["rho_vec_T"] = np.diagonal(o._R[T]).copy()
+        out.update({tag + "_" + k: v for k, v in dict(Y=Ymat, C0=C0, theta0=theta0.reshape(-1), V0=V0, mu0=mu0.reshape(-1), P0=P0, Q=Q,
+                                                      rho_vec=rho_vec, lam0=1.8, gradsum=o._gradsum.reshape(-1), **res).items()})
+    # masked flat functions with a non-uniform diagonal R
+    common = ref_loader.impute_module("common")
+    Yorig = np.genfromtxt(os.path.join(REF, "ExperimentImpute", "data", "LondonAir_PM25.csv"), delimiter=",")[:, :500]
+    np.random.seed(123)
+    rr = 10
+    Y, M, Mmiss, C, X, _ = _impute_inputs(common, Yorig, 30, rr)
+    dd, n = Y.shape
+    YorigInt = np.copy(Yorig); YorigInt[np.isnan(YorigInt)] = 0
+    rho_i = 5.0 + 10.0 * np.random.rand(dd)
+    out.update(imp_Yorig=Yorig, imp_Mmiss=Mmiss.astype(np.uint8), imp_C0=C, imp_X0=X, imp_rho_vec=rho_i)
+    for method in ("rPSMF", "PSMF"):
+        mod = ref_loader.impute_module(method)
+        V = 2 * np.eye(rr); Qm = 0.1 * np.eye(rr); R = np.diag(rho_i); P = np.eye(rr)
+        Xw = X.copy()
+        Einit = mod.RMSEM(C @ Xw, YorigInt, Mmiss)
+        if method == "rPSMF":
+            ep, ef, rt, ib = mod.robust_PSMF.func(Y, C, Xw, dd, n, rr, M, Mmiss, V, Qm, R, P, 1.8, 2, 2, YorigInt, Einit)
+        else:
+            ep, ef, rt, ib = mod.ProbabilisticSequentialMatrixFactorizer.func(Y, C, Xw, dd, n, rr, M, Mmiss, 0, V, Qm, R, P, 2, 2, YorigInt, Einit)
+        out.update({"imp_%s_%s" % (method, k): v for k, v in dict(Einit=Einit, Epred=ep, Efull=ef, inside=ib, X_final=Xw).items()})
+    np.savez_compressed(os.path.join(HERE, "diag_R_cases.npz"), **out)
+    print("wrote diag_R_cases", os.path.getsize(os.path.join(HERE, "diag_R_cases.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found at %s" % REF)
-    which = sys.argv[1:] or ["pm25", "pm10", "sp500", "pypsmf", "recursive"]
+    which = sys.argv[1:] or ["pm25", "pm10", "sp500", "pypsmf", "recursive", "linear", "diagR"]
     if "pm25" in which:
         make_impute("impute_pm25_30", "LondonAir_PM25.csv", 30, None, 1,
                     published="LondonAir_PM25_30_%s.json")
@@ -253,3 +342,7 @@ if __name__ == "__main__":
         make_pypsmf()
     if "recursive" in which:
         make_recursive()
+    if "linear" in which:
+        make_linear()
+    if "diagR" in which:
+        make_diagR()

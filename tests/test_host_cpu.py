@@ -30,12 +30,15 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from rpsmf_b200 import _capi
-    # psmf_config: 2 x int64, 10 x int32, 2 x double; psmf_io: 14 pointer/int64 slots
-    assert ctypes.sizeof(_capi.PsmfConfig) == 2 * 8 + 10 * 4 + 2 * 8
-    assert ctypes.sizeof(_capi.PsmfIO) == 14 * 8
+    # psmf_config: 2 x int64, 10 x int32, 2 x double, 2 x int32; psmf_io: 20 pointer / int64 / double slots
+    assert ctypes.sizeof(_capi.PsmfConfig) == 2 * 8 + 10 * 4 + 2 * 8 + 2 * 4
+    assert ctypes.sizeof(_capi.PsmfIO) == 20 * 8
     hdr = open(os.path.join(ROOT, "include", "psmf_b200.h")).read()
     for flag, val in (("PSMF_ROBUST", _capi.ROBUST), ("PSMF_SIMPLIFIED", _capi.SIMPLIFIED), ("PSMF_CUPDATE_VT", _capi.CUPDATE_VT),
-                      ("PSMF_FIXED_LAMBDA", _capi.FIXED_LAMBDA), ("PSMF_LL_STUDENT", _capi.LL_STUDENT),
+                      ("PSMF_FIXED_LAMBDA", _capi.FIXED_LAMBDA), ("PSMF_LL_STUDENT", _capi.LL_STUDENT), ("PSMF_NAN_MASK", _capi.NAN_MASK),
+                      ("PSMF_DYN_LINEAR", _capi.DYN_LINEAR), ("PSMF_KERNEL_BATCH", _capi.KERNEL_BATCH), ("PSMF_XCHG_EXTERNAL", _capi.XCHG_EXTERNAL),
+                      ("PSMF_NEVAL", _capi.NEVAL), ("PSMF_EVAL_INSIDE", _capi.EVAL_INSIDE), ("PSMF_EVAL_COUNT", _capi.EVAL_COUNT),
+                      ("PSMF_MAILBOX_BLOB_BYTES", _capi.MAILBOX_BLOB_BYTES),
                       ("PSMF_DYN_COS", _capi.DYN_COS), ("PSMF_DYN_EXTERNAL", _capi.DYN_EXTERNAL), ("PSMF_NSCAL", _capi.NSCAL)):
         m = re.search(r"#define\s+%s\s+(\d+)" % flag, hdr)
         assert m and int(m.group(1)) == val, flag
@@ -136,7 +139,7 @@ def test_plain_c_caller_compiles_and_links():
     with tempfile.TemporaryDirectory() as tmp:
         probe = os.path.join(tmp, "probe.c")
         with open(probe, "w") as fp:
-            fp.write('#include "psmf_b200.h"\nint main(void) { return sizeof(psmf_config) == 72 && sizeof(psmf_io) == 112 ? 0 : 1; }\n')
+            fp.write('#include "psmf_b200.h"\nint main(void) { return sizeof(psmf_config) == 80 && sizeof(psmf_io) == 160 ? 0 : 1; }\n')
         subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), probe,
                         "-o", os.path.join(tmp, "probe")], check=True)
         assert subprocess.run([os.path.join(tmp, "probe")]).returncode == 0
@@ -146,23 +149,59 @@ def test_plain_c_caller_compiles_and_links():
                        check=True)
 
 
-def test_bench_segment_mask_generator():
-    """bench.py --mask segments: runs of 20 missing steps per row until the requested ratio (common.py:50-76)."""
+def test_bench_generator_is_N_invariant_and_segment_mask():
+    """bench_data.py: every value is a function of (seed, global time, global row), so a row shard generated by any
+    rank of any world size equals the same rows of the single-GPU problem -- bench.py relies on it for the parity
+    prologue and for the N-independent X checksum.  --mask segments: runs of 20 missing steps per row until the
+    requested GLOBAL ratio (common.py:50-76)."""
     import os
     import sys
     import torch
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import bench
-    g = torch.Generator(device="cpu"); g.manual_seed(1)
-    M = bench.segment_mask(torch, torch.device("cpu"), 600, 40, 0.2, g)
-    assert M.shape == (600, 40) and M.dtype == torch.uint8
-    ratio = 1.0 - M.float().mean().item()
-    assert 0.2 <= ratio < 0.26
-    assert M[0].all()                                   # segments start at t >= 1
-    for c in (0, 3, 39):                                # every maximal missing run is a union of 20-step segments
-        miss = np.concatenate([[0], (M[:, c].numpy() == 0).astype(int), [0]])
-        edges = np.flatnonzero(np.diff(miss))
+    import bench_data as bd
+    cpu = torch.device("cpu")
+    d, r, T = 96, 4, 130
+    Y, M, C0, x0 = bd.make_series(torch, cpu, d, 0, d, r, T, torch.float64, chunk=50)
+    assert M.dtype == torch.uint8 and (Y[M == 0] == 0).all()
+    miss = 1.0 - M.float().mean().item()
+    assert 0.15 < miss < 0.25
+    parts = [bd.make_series(torch, cpu, b - a, a, d, r, T, torch.float64, chunk=64) for a, b in ((0, 32), (32, 96))]
+    assert torch.equal(torch.cat([p[0] for p in parts], 1), Y) and torch.equal(torch.cat([p[1] for p in parts], 1), M)
+    assert torch.equal(torch.cat([p[2] for p in parts], 0), C0) and torch.equal(parts[0][3], x0) and torch.equal(parts[1][3], x0)
+    # a later window of the same problem (t0 > 0) continues the same sequence
+    Yw, Mw, _, _ = bd.make_series(torch, cpu, d, 0, d, r, 30, torch.float64, t0=100)
+    assert torch.equal(Yw, Y[100:]) and torch.equal(Mw, M[100:])
+    # NaN encoding carries the same mask and values
+    Yn, Mn, _, _ = bd.make_series(torch, cpu, d, 0, d, r, T, torch.float64, nan_encoded=True)
+    assert Mn is None and torch.equal(torch.isnan(Yn), M == 0) and torch.equal(torch.nan_to_num(Yn, nan=0.0), Y)
+    # noise is heavy-tailed but sane, dictionary ~ N(0, 1), init ~ U[0, 1)
+    assert 0.0 <= float(C0.min()) and float(C0.max()) < 1.0 and abs(float(C0.mean()) - 0.5) < 0.1
+    # segment mask: global ratio reached, runs of >= 20 steps, starts at t >= 1, and N-invariant through the all-reduce hook
+    Ms = bd.segment_mask(torch, cpu, 600, 0, 40, 40, 0.2)
+    ratio = 1.0 - Ms.float().mean().item()
+    assert 0.2 <= ratio < 0.26 and Ms[0].all()
+    for c in (0, 3, 39):
+        mm = np.concatenate([[0], (Ms[:, c].numpy() == 0).astype(int), [0]])
+        edges = np.flatnonzero(np.diff(mm))
         runs = edges[1::2] - edges[0::2]
         assert runs.size > 0 and runs.min() >= 20
-    Y, M2, C0, x0 = bench.make_device_data(torch, torch.device("cpu"), 40, 0, 40, 4, 300, torch.float64, mask="segments")
-    assert ((Y == 0) | (M2 == 1)).all() and (Y[M2 == 0] == 0).all()
+    # two "ranks" in lock step: each sweep sees the global count
+    import threading
+    halves, box, bar = [None, None], [None, None], threading.Barrier(2)
+
+    def rank(k):
+        def allreduce(v):
+            box[k] = v.clone()
+            bar.wait()
+            tot = box[0] + box[1]
+            bar.wait()
+            return tot
+        halves[k] = bd.segment_mask(torch, cpu, 600, 20 * k, 20, 40, 0.2, allreduce=allreduce)
+    th = [threading.Thread(target=rank, args=(k,)) for k in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert torch.equal(torch.cat(halves, 1), Ms)
+    # batch generator: a series depends on its global index only
+    Yb, Mb, Cb, xb = bd.make_batch(torch, cpu, 0, 6, 6, 32, 3, 20, torch.float64, series_chunk=4)
+    Y2, M2, C2, x2 = bd.make_batch(torch, cpu, 2, 3, 6, 32, 3, 20, torch.float64)
+    assert torch.equal(Y2, Yb[2:5]) and torch.equal(M2, Mb[2:5]) and torch.equal(C2, Cb[2:5]) and torch.equal(x2, xb[2:5])

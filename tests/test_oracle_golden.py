@@ -174,3 +174,58 @@ def test_c_oracle_matches_numpy_oracle(robust):
     assert relerr(res["X"], X) < TOL and relerr(res["C"], st.C) < TOL
     assert relerr(res["P"], st.P) < TOL and relerr(res["V"], st.V) < TOL
     assert relerr(res["rho"], st.rho) < TOL and relerr(res["lam"], st.lam) < TOL
+
+
+# ---------------------------------------------------------------------------
+# round 2: linear dynamics + forecast, and diagonal non-uniform R, pinned against the unmodified reference
+# (fixtures: tests/golden/make_golden.py make_linear / make_diagR)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,robust", [("lin_psmf", False), ("lin_rpsmf", True)])
+def test_oracle_linear_dynamics_and_predict(tag, robust):
+    g = load_golden("pypsmf_linear")
+    Y = g[tag + "_Y"]
+    T, d = Y.shape
+    cfg = po.OracleConfig(robust=robust, dynamics=po.DYN_LINEAR, lin_A=g[tag + "_A"], lin_c=g[tag + "_c"])
+    st = po.OracleState(g[tag + "_C0"].copy(), g[tag + "_mu0"].copy(), g[tag + "_P0"].copy(), g[tag + "_V0"].copy(),
+                        g[tag + "_Q"].copy(), float(g[tag + "_rho"]), float(g[tag + "_lam0"]) if robust else 0.0)
+    st, X, Yrec, scal = po.run(st, cfg, Y, None, k0=1)
+    assert relerr(Yrec, g[tag + "_ypred"]) < 1e-9
+    assert relerr(st.C, g[tag + "_C"]) < 1e-9 and relerr(st.x, g[tag + "_mu"]) < 1e-9
+    assert relerr(st.P, g[tag + "_P"]) < 1e-9 and relerr(st.V, g[tag + "_V"]) < 1e-9
+    mus, yp = po.predict(st, cfg, T, g[tag + "_ypred_future"].shape[0])
+    assert relerr(mus, g[tag + "_mu_future"]) < 1e-9 and relerr(yp, g[tag + "_ypred_future"]) < 1e-9
+
+
+@pytest.mark.parametrize("tag,robust", [("diag_psmf", False), ("diag_rpsmf", True)])
+def test_oracle_diagonal_nonuniform_R_classes(tag, robust):
+    g = load_golden("diag_R_cases")
+    Y = g[tag + "_Y"]
+    cfg = po.OracleConfig(robust=robust, dynamics=po.DYN_COS)
+    st = po.OracleState(g[tag + "_C0"].copy(), g[tag + "_mu0"].copy(), g[tag + "_P0"].copy(), g[tag + "_V0"].copy(),
+                        g[tag + "_Q"].copy(), g[tag + "_rho_vec"].copy(), float(g[tag + "_lam0"]) if robust else 0.0,
+                        g[tag + "_theta0"].copy())
+    st, X, Yrec, scal = po.run(st, cfg, Y, None, k0=1)
+    assert relerr(Yrec, g[tag + "_ypred"]) < 1e-9
+    assert relerr(st.C, g[tag + "_C"]) < 1e-9 and relerr(st.x, g[tag + "_mu"]) < 1e-9
+    assert relerr(st.P, g[tag + "_P"]) < 1e-9 and relerr(st.V, g[tag + "_V"]) < 1e-9
+    if robust:
+        assert relerr(st.rho, g[tag + "_rho_vec_T"]) < 1e-9 and abs(st.lam - float(g[tag + "_lam_T"])) < 1e-9 * st.lam
+
+
+@pytest.mark.parametrize("method", ["rPSMF", "PSMF"])
+def test_oracle_diagonal_nonuniform_R_impute(method):
+    g = load_golden("diag_R_cases")
+    Yorig = g["imp_Yorig"]
+    Mmiss = g["imp_Mmiss"].astype(np.float64)
+    Ymiss = Yorig.copy(); Ymiss[Mmiss == 1] = np.nan
+    M = (~np.isnan(Ymiss)).astype(np.int64)
+    Y = Ymiss.copy(); Y[np.isnan(Y)] = 0
+    YorigInt = Yorig.copy(); YorigInt[np.isnan(YorigInt)] = 0
+    r = g["imp_C0"].shape[1]
+    X = g["imp_X0"].copy()
+    pre = "imp_%s_" % method
+    ep, ef, ib, st, *_ = po.impute_fit(Y, g["imp_C0"], X, M, Mmiss, 2 * np.eye(r), 0.1 * np.eye(r), g["imp_rho_vec"], np.eye(r), 1.8, 2, 2,
+                                       YorigInt, float(g[pre + "Einit"]), robust=method == "rPSMF")
+    assert relerr(ep, g[pre + "Epred"]) < 1e-9 and relerr(ef, g[pre + "Efull"]) < 1e-9
+    assert abs(ib - float(g[pre + "inside"])) < 1e-12
+    assert relerr(X, g[pre + "X_final"]) < 1e-9
