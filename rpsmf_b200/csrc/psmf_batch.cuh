@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(NW * 32, batch_min_ctas(R, NW)) psmf_batch_ker
         const T* __restrict__ Yo_t = evalon ? reinterpret_cast<const T*>(p.Yorig) + (int64_t)series * p.ysst + t * p.ldy : nullptr;
         const uint8_t* __restrict__ Et = evalon ? p.E + (int64_t)series * p.esst + t * p.lde : nullptr;
         const double w1 = sh.w1, w0 = sh.w0;
+        stamp(p, t, 0);
         TileAcc<R> acc;
         acc.zero();
         // the current values leave the prefetch registers, the loads of step t+1 take their place
@@ -165,8 +166,10 @@ __global__ void __launch_bounds__(NW * 32, batch_min_ctas(R, NW)) psmf_batch_ker
             tile_gram<R, T>(acc, tl, mbits, lane);               // straight from the resident tile
             __syncwarp();
         }
+        stamp(p, t, 1);
         acc_writeout<R>(acc, red + warp * NSP, w1, lane);
         __syncthreads();
+        stamp(p, t, 2);
         if (tid < NST) {                                         // CTA total: fixed order over the warps
             double s = 0.0;
 #pragma unroll
@@ -182,7 +185,9 @@ __global__ void __launch_bounds__(NW * 32, batch_min_ctas(R, NW)) psmf_batch_ker
             }
         }
         __syncthreads();
+        stamp(p, t, 5);
         small_update<R, NGJ>(p, sh, tid, lane, warp, series, t, true, NTHR);
+        stamp(p, t, 6);
     }
 
     // pending rank-1 update of the last step, then C goes back to HBM with one bulk store
