@@ -122,7 +122,7 @@ struct psmf_engine {
 
 static std::string g_create_error;
 
-static size_t mbox_bytes() { return (size_t)2 * PSMF_MAX_PEERS * MBOX_SLOT * 16; }   // [2 parities][peers] slots of MBOX_SLOT cells
+static size_t mbox_bytes() { return (size_t)4 * PSMF_MAX_PEERS * MBOX_SLOT * 16; }   // [MBOX_DEPTH][peers] slots of MBOX_SLOT cells
 
 static int fail(psmf_engine* h, int code, const std::string& msg) {
     if (h)
@@ -477,7 +477,8 @@ static int run_impl(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k
     if (phase != 2) CK(h, cudaMemsetAsync(h->status, 0xFF, sizeof(long long), st));
     // ---- which kernel ----
     // the resident batch kernel: independent series / one small series, C in shared memory for the whole launch
-    bool use3 = h->batch_ok && !external && (h->cfg.kernel == 3 || (h->cfg.kernel == 0 && (h->S > 1 || h->ntiles <= 32)));
+    bool use3 = h->batch_ok && !external &&
+                (h->cfg.kernel == 3 || (h->cfg.kernel == 0 && h->cfg.ctas <= 0 && (h->S > 1 || h->ntiles <= 32)));
     size_t dyn3 = h->dyn_smem3;
     if (use3 && eval) {
         dyn3 = batch_dyn(h->ntiles, h->R, h->esize, true);

@@ -117,6 +117,13 @@ struct Spin {
     }
 };
 
+// pollers share their SM with warps that do arithmetic (the solvers of the control CTA, the pass warps of a data CTA):
+// a short sleep after a failed attempt keeps them out of the issue slots; it adds at most this much to the wake-up
+#ifndef PSMF_POLL_BACKOFF_NS
+#define PSMF_POLL_BACKOFF_NS 40
+#endif
+constexpr unsigned POLL_BACKOFF_NS = PSMF_POLL_BACKOFF_NS;
+template <bool BACKOFF = true>
 __device__ __forceinline__ double cell_poll(const KParams& p, const uint4* cell, uint32_t tag, long long step) {
     uint32_t lo, t0, hi, t1;
     Spin sp;
@@ -124,6 +131,7 @@ __device__ __forceinline__ double cell_poll(const KParams& p, const uint4* cell,
         asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(cell) : "memory");
         if (t0 == tag && t1 == tag) break;
         if (sp.expired(p, SPIN_CELL, step)) break;
+        if (BACKOFF && POLL_BACKOFF_NS > 0) __nanosleep(POLL_BACKOFF_NS);
     }
     return __hiloint2double((int)hi, (int)lo);
 }
@@ -629,37 +637,93 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
 // same order on every GPU, so the replicated state stays bit-identical.  No fence and no flag: the latency
 // is one NVLink store plus one local poll.  Two parities make the mailbox safe without a handshake: a GPU
 // can only be one step ahead of its slowest peer (it needs that peer's cells of the current step to proceed).
+// Sum of one statistics entry over all GPUs in RANK ORDER (bit-identical on every GPU): the peers' contributions are
+// tagged cells of the local mailbox, polled CONCURRENTLY -- all outstanding loads are issued before any tag is looked at, so
+// the wait costs one round trip however many peers there are (a per-peer poll loop costs one round trip per peer).
+// local_cell != nullptr: this GPU's own contribution is a tagged cell as well (gpu scope, tag ltag), else it is `own`.
+__device__ __forceinline__ double gather_ranks(const KParams& p, const uint4* __restrict__ slots /* [MAX_PEERS][MBOX_SLOT] */, int e,
+                                               uint32_t xtag, const uint4* local_cell, uint32_t ltag, double own, long long step) {
+    if (p.world == 1) return local_cell != nullptr ? cell_poll(p, local_cell, ltag, step) : own;
+    double v[MAX_PEERS];
+    unsigned pending = (1u << p.world) - 1u;
+    if (local_cell == nullptr) pending &= ~(1u << p.rank);
+    Spin sp;
+    while (pending != 0u) {
+        uint32_t lo[MAX_PEERS], hi[MAX_PEERS], t0[MAX_PEERS], t1[MAX_PEERS];
+#pragma unroll
+        for (int s = 0; s < MAX_PEERS; ++s) {
+            lo[s] = hi[s] = t0[s] = t1[s] = 0u;
+            if ((pending >> s) & 1u) {
+                if (s == p.rank)
+                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(lo[s]), "=r"(t0[s]), "=r"(hi[s]), "=r"(t1[s]) : "l"(local_cell) : "memory");
+                else
+                    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(lo[s]), "=r"(t0[s]), "=r"(hi[s]), "=r"(t1[s]) : "l"(slots + (size_t)s * MBOX_SLOT + e) : "memory");
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < MAX_PEERS; ++s) {
+            const uint32_t want = s == p.rank ? ltag : xtag;
+            if (((pending >> s) & 1u) && t0[s] == want && t1[s] == want) {
+                v[s] = __hiloint2double((int)hi[s], (int)lo[s]);
+                pending &= ~(1u << s);
+            }
+        }
+        if (pending != 0u) {
+            if (sp.expired(p, SPIN_PEER, step)) break;
+            if (POLL_BACKOFF_NS > 0) __nanosleep(POLL_BACKOFF_NS);   // leave the issue slots to the warps that do arithmetic on this SM
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int s = 0; s < MAX_PEERS; ++s)
+        if (s < p.world) sum += (local_cell == nullptr && s == p.rank) ? own : v[s];
+    return sum;
+}
+
+// Mailbox depth.  A slot is reused MBOX_DEPTH steps later; with two filter steps in flight (pipelined kernel) a GPU can
+// publish step t+2 before a slow peer has read step t, but never step t+4: that needs its own solve of t+2, hence the
+// peer's statistics of t+2, hence the peer's solve of t -- which has read the cells of step t.
+constexpr int MBOX_DEPTH = 4;
+
+// header cell of a mailbox slot: {kernel id, statistics count}; exchanged once per launch (step 0) by one thread
+__device__ __forceinline__ void mailbox_check_peers(const KParams& p, int kernel_id, int nst, int64_t t) {
+    const unsigned long long step = p.step_base + (unsigned long long)t;
+    const int slot = (int)(step % MBOX_DEPTH);
+    const uint32_t tag = tag_of(step + 1ULL);
+    const double header = (double)(kernel_id * 4096 + nst);
+    for (int pr = 0; pr < p.world; ++pr)
+        if (pr != p.rank)
+            cell_store_sys(reinterpret_cast<uint4*>(p.mbox_peer[pr]) + ((size_t)slot * MAX_PEERS + p.rank) * MBOX_SLOT + MBOX_SLOT - 1, header, tag);
+    const uint4* local = reinterpret_cast<const uint4*>(p.mbox_local) + (size_t)slot * MAX_PEERS * MBOX_SLOT;
+    for (int src = 0; src < p.world; ++src)
+        if (src != p.rank && cell_poll_sys(p, local + (size_t)src * MBOX_SLOT + MBOX_SLOT - 1, tag, t) != header) {
+            // all ranks must run the same kernel with the same statistics vector (the host agrees on it in
+            // psmf_mailbox_connect); a mismatch would add unrelated numbers: flag it instead
+            if (*reinterpret_cast<volatile unsigned long long*>(p.bar + ABORT_WORD) == 0ULL)
+                atomicCAS((unsigned long long*)p.status, ~0ULL, (unsigned long long)STATUS_MISMATCH | (unsigned long long)t);
+        }
+}
+
 template <int NST, int NSP, int BAR = 0>
 __device__ __forceinline__ void gpu_exchange(const KParams& p, double* __restrict__ tot, double* __restrict__ /*tmp*/, int tid,
                                              int64_t t, int part, int nthr, int kernel_id) {
     const unsigned long long step = p.step_base + (unsigned long long)t;
-    const int parity = (int)(step & 1ULL);
+    const int slot = (int)(step % MBOX_DEPTH);
     const uint32_t tag = tag_of(step + 1ULL);
-    const double header = (double)(kernel_id * 4096 + NST);          // what this GPU sends: kernel and statistics layout
     if (part == 0) {
-        for (int e = tid; e <= NST; e += nthr) {
-            const double v = e < NST ? tot[e] : header;
-            const int cell = e < NST ? e : MBOX_SLOT - 1;
+        for (int e = tid; e < NST; e += nthr) {
+            const double v = tot[e];
             for (int pr = 0; pr < p.world; ++pr)
                 if (pr != p.rank)
-                    cell_store_sys(reinterpret_cast<uint4*>(p.mbox_peer[pr]) + ((size_t)parity * MAX_PEERS + p.rank) * MBOX_SLOT + cell, v, tag);
+                    cell_store_sys(reinterpret_cast<uint4*>(p.mbox_peer[pr]) + ((size_t)slot * MAX_PEERS + p.rank) * MBOX_SLOT + e, v, tag);
         }
+        if (t == 0 && tid == nthr - 1) mailbox_check_peers(p, kernel_id, NST, t);
     }
-    const uint4* local = reinterpret_cast<const uint4*>(p.mbox_local) + (size_t)parity * MAX_PEERS * MBOX_SLOT;
-    if (tid == nthr - 1) {
-        // all ranks must run the same kernel with the same statistics vector (the host agrees on it in
-        // psmf_mailbox_connect); a mismatch would add unrelated numbers: flag it instead
-        for (int src = 0; src < p.world; ++src)
-            if (src != p.rank && cell_poll_sys(p, local + (size_t)src * MBOX_SLOT + MBOX_SLOT - 1, tag, t) != header) {
-                if (*reinterpret_cast<volatile unsigned long long*>(p.bar + ABORT_WORD) == 0ULL)
-                    atomicCAS((unsigned long long*)p.status, ~0ULL, (unsigned long long)STATUS_MISMATCH | (unsigned long long)t);
-            }
-    }
-    for (int e = tid; e < NST; e += nthr) {
-        double s = 0.0;
-        for (int src = 0; src < p.world; ++src) s += (src == p.rank) ? tot[e] : cell_poll_sys(p, local + (size_t)src * MBOX_SLOT + e, tag, t);
-        tot[e] = s;                                              // entry e is read and written by this thread only
-    }
+    const uint4* local = reinterpret_cast<const uint4*>(p.mbox_local) + (size_t)slot * MAX_PEERS * MBOX_SLOT;
+    for (int e = tid; e < NST; e += nthr)
+        tot[e] = gather_ranks(p, local, e, tag, nullptr, 0u, tot[e], t);      // entry e is read and written by this thread only
     sync_n<BAR>(nthr);
 }
 

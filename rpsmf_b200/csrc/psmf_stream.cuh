@@ -494,34 +494,72 @@ __device__ void reduce_warp(const KParams& p, DataSmem<R>& ps, int lane, int NPW
             if (lane == 0) stamp_pass(p, t, 9, 0, true);
             __syncwarp();
         }
-        // (2) this CTA's share of the grid reduction: entries cta, cta + ndata, .. summed over all CTAs.  The warp
-        // polls the cells of one entry together (one L2 round trip per attempt), lanes over the CTAs.
-        for (int e = cta; e < NST2; e += ndata) {
+        // (2) this CTA's share of the grid reduction: entries cta, cta + ndata, .. summed over all CTAs.  The warp polls
+        // the cells of up to TWO entries together (lanes over the CTAs; all loads of both rows are in flight before any tag
+        // is examined): one L2 round trip per attempt whether the CTA owns one entry or two.  Each total goes to the local
+        // control CTA and -- row sharding -- straight into the mailbox of every peer GPU (lane = destination rank), so the
+        // NVLink hop runs next to the local L2 hop instead of behind it.
+        const unsigned long long gstep = p.step_base + (unsigned long long)t;
+        const int mslot = (int)(gstep % MBOX_DEPTH);
+        const uint32_t xtag = tag_of(gstep + 1ULL);
+        const int nj = (ndata + 31) >> 5;                          // 32-cell groups per entry row (<= 8)
+        for (int e = cta; e < NST2; e += 2 * ndata) {
+            const int e2 = e + ndata;
+            const bool has2 = e2 < NST2;
             const uint4* row = base + (size_t)e * pstr;
-            double v[8];
+            const uint4* row2 = base + (size_t)(has2 ? e2 : e) * pstr;
+            double v[8], w[8];
             bool ok;
             Spin sp;
             do {
                 ok = true;
+                uint32_t lo[8], hi[8], t0[8], t1[8], lo2[8], hi2[8], t02[8], t12[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    lo[j] = hi[j] = lo2[j] = hi2[j] = 0u;
+                    t0[j] = t1[j] = t02[j] = t12[j] = ptag;
+                    if (j < nj) {
+                        const int c = min(lane + 32 * j, pstr - 1);
+                        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(lo[j]), "=r"(t0[j]), "=r"(hi[j]), "=r"(t1[j]) : "l"(row + c) : "memory");
+                        if (has2)
+                            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(lo2[j]), "=r"(t02[j]), "=r"(hi2[j]), "=r"(t12[j]) : "l"(row2 + c) : "memory");
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = lane + 32 * j;
-                    uint32_t lo, t0, hi, t1;
-                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(row + min(c, pstr - 1)) : "memory");
-                    ok = ok && (c >= ndata || (t0 == ptag && t1 == ptag));
-                    v[j] = (c < ndata) ? __hiloint2double((int)hi, (int)lo) : 0.0;
+                    const bool in = c < ndata;
+                    ok = ok && (!in || (t0[j] == ptag && t1[j] == ptag && t02[j] == ptag && t12[j] == ptag));
+                    v[j] = in ? __hiloint2double((int)hi[j], (int)lo[j]) : 0.0;
+                    w[j] = in ? __hiloint2double((int)hi2[j], (int)lo2[j]) : 0.0;
                 }
-                if (!ok && sp.expired(p, SPIN_PARTIALS, t)) ok = true;
+                if (!ok) {
+                    if (sp.expired(p, SPIN_PARTIALS, t)) ok = true;
+                    else if (POLL_BACKOFF_NS > 0) __nanosleep(POLL_BACKOFF_NS);
+                }
             } while (!__all_sync(FULL, ok));
             const double sum = warp_allsum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])));
-            if (lane == 0) cell_store(totals + (size_t)b * NSP2 + e, sum, tag_of((unsigned long long)t + 1ULL));
+            const double sum2 = has2 ? warp_allsum(((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]))) : 0.0;
+            if (lane < p.world) {
+                if (lane == p.rank) {
+                    cell_store(totals + (size_t)b * NSP2 + e, sum, tag_of((unsigned long long)t + 1ULL));
+                    if (has2) cell_store(totals + (size_t)b * NSP2 + e2, sum2, tag_of((unsigned long long)t + 1ULL));
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>(p.mbox_peer[lane]) + ((size_t)mslot * MAX_PEERS + p.rank) * MBOX_SLOT;
+                    cell_store_sys(dst + e, sum, xtag);
+                    if (has2) cell_store_sys(dst + e2, sum2, xtag);
+                }
+            }
             __syncwarp();
         }
     }
 }
 
-// ---- reducer half of the control CTA: collect the totals, NVLink exchange, hand over to the solvers -----
+// ---- reducer half of the control CTA: gather every entry over the local reduce warps and the peer GPUs ---------
+// Thread e polls the local total of entry e and the world - 1 mailbox cells the peers' reduce warps stored, all at once
+// (gather_ranks), and adds them in rank order: the same order on every GPU, so the replicated state stays bit-identical.
 template <int R>
 __device__ void control_reduce(const KParams& p, ControlSmem<R>& cs) {
     constexpr int NSP2 = nstat2_pad(R), NST2 = nstat2(R);
@@ -533,10 +571,13 @@ __device__ void control_reduce(const KParams& p, ControlSmem<R>& cs) {
         double* tot2 = cs.tot2[b];
         if (t >= 2) named_bar_sync(CB_EMPTY + b, (int)blockDim.x);   // the solvers are done with the sums of step t-2
         stamp(p, t, 2, C_SOLVERS);
-        for (int e = tid; e < NST2; e += NTHR) tot2[e] = cell_poll(p, totals + (size_t)b * NSP2 + e, tag_of((unsigned long long)t + 1ULL), t);
-        sync_n<CB_R>(NTHR);
+        const unsigned long long gstep = p.step_base + (unsigned long long)t;
+        const uint4* slots = reinterpret_cast<const uint4*>(p.mbox_local) + (size_t)(gstep % MBOX_DEPTH) * MAX_PEERS * MBOX_SLOT;
+        for (int e = tid; e < NST2; e += NTHR)
+            tot2[e] = gather_ranks(p, slots, e, tag_of(gstep + 1ULL), totals + (size_t)b * NSP2 + e, tag_of((unsigned long long)t + 1ULL), 0.0, t);
+        if (p.world > 1 && t == 0 && tid == NTHR - 1) mailbox_check_peers(p, 2, NST2, t);
         stamp(p, t, 4, C_SOLVERS);
-        if (p.world > 1) gpu_exchange<NST2, NSP2, CB_R>(p, tot2, cs.tmp2, tid, t, 0, NTHR, 2);
+        sync_n<CB_R>(NTHR);
         stamp(p, t, 13, C_SOLVERS);
         __threadfence_block();
         named_bar_arrive(CB_FULL + b, (int)blockDim.x);
@@ -818,7 +859,7 @@ template <int R>
 __device__ __forceinline__ void fetch_params(const KParams& p, DataSmem<R>& ps, int64_t set, int wp, int lane) {
     if (wp == 0) {
         const uint4* cells = reinterpret_cast<const uint4*>(p.gparams) + (size_t)(set & 1) * 2 * R;
-        for (int i = lane; i < 2 * R; i += 32) ps.par[set & 1][i] = cell_poll(p, cells + i, tag_of((unsigned long long)set + 1ULL), set);
+        for (int i = lane; i < 2 * R; i += 32) ps.par[set & 1][i] = cell_poll<false>(p, cells + i, tag_of((unsigned long long)set + 1ULL), set);   // the whole CTA waits on this: no backoff
         __threadfence_block();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ps.par_full[set & 1]);
