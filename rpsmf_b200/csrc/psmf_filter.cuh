@@ -644,33 +644,38 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
 __device__ __forceinline__ double gather_ranks(const KParams& p, const uint4* __restrict__ slots /* [MAX_PEERS][MBOX_SLOT] */, int e,
                                                uint32_t xtag, const uint4* local_cell, uint32_t ltag, double own, long long step) {
     if (p.world == 1) return local_cell != nullptr ? cell_poll(p, local_cell, ltag, step) : own;
+    // every index below is a compile-time constant after unrolling (the rank only enters through bit masks and selects):
+    // the values stay in registers
     double v[MAX_PEERS];
-    unsigned pending = (1u << p.world) - 1u;
-    if (local_cell == nullptr) pending &= ~(1u << p.rank);
+#pragma unroll
+    for (int s = 0; s < MAX_PEERS; ++s) v[s] = 0.0;
+    unsigned pending = ((1u << p.world) - 1u) & ~(1u << p.rank);        // peers still missing
+    bool lpend = local_cell != nullptr;                                 // own contribution still missing
     Spin sp;
-    while (pending != 0u) {
+    while (pending != 0u || lpend) {
         uint32_t lo[MAX_PEERS], hi[MAX_PEERS], t0[MAX_PEERS], t1[MAX_PEERS];
+        uint32_t llo = 0u, lhi = 0u, lt0 = 0u, lt1 = 0u;
+        if (lpend)
+            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(llo), "=r"(lt0), "=r"(lhi), "=r"(lt1) : "l"(local_cell) : "memory");
 #pragma unroll
         for (int s = 0; s < MAX_PEERS; ++s) {
-            lo[s] = hi[s] = t0[s] = t1[s] = 0u;
-            if ((pending >> s) & 1u) {
-                if (s == p.rank)
-                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(lo[s]), "=r"(t0[s]), "=r"(hi[s]), "=r"(t1[s]) : "l"(local_cell) : "memory");
-                else
-                    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(lo[s]), "=r"(t0[s]), "=r"(hi[s]), "=r"(t1[s]) : "l"(slots + (size_t)s * MBOX_SLOT + e) : "memory");
-            }
+            lo[s] = 0u; hi[s] = 0u; t0[s] = 0u; t1[s] = 0u;
+            if ((pending >> s) & 1u)
+                asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(lo[s]), "=r"(t0[s]), "=r"(hi[s]), "=r"(t1[s]) : "l"(slots + (size_t)s * MBOX_SLOT + e) : "memory");
+        }
+        if (lpend && lt0 == ltag && lt1 == ltag) {
+            own = __hiloint2double((int)lhi, (int)llo);
+            lpend = false;
         }
 #pragma unroll
         for (int s = 0; s < MAX_PEERS; ++s) {
-            const uint32_t want = s == p.rank ? ltag : xtag;
-            if (((pending >> s) & 1u) && t0[s] == want && t1[s] == want) {
+            if (((pending >> s) & 1u) && t0[s] == xtag && t1[s] == xtag) {
                 v[s] = __hiloint2double((int)hi[s], (int)lo[s]);
                 pending &= ~(1u << s);
             }
         }
-        if (pending != 0u) {
+        if (pending != 0u || lpend) {
             if (sp.expired(p, SPIN_PEER, step)) break;
             if (POLL_BACKOFF_NS > 0) __nanosleep(POLL_BACKOFF_NS);   // leave the issue slots to the warps that do arithmetic on this SM
         }
@@ -678,7 +683,7 @@ __device__ __forceinline__ double gather_ranks(const KParams& p, const uint4* __
     double sum = 0.0;
 #pragma unroll
     for (int s = 0; s < MAX_PEERS; ++s)
-        if (s < p.world) sum += (local_cell == nullptr && s == p.rank) ? own : v[s];
+        if (s < p.world) sum += (s == p.rank) ? own : v[s];             // rank order: the same on every GPU
     return sum;
 }
 

@@ -106,13 +106,32 @@ def _torchrun(nproc, port, *extra, env=None, timeout=600):
 
 
 @pytest.mark.gpu
-def test_row_sharded_filter_two_ranks_one_gpu():
-    """The N > 1 CUDA path where only ONE GPU is leased: two ranks share cuda:0, their persistent kernels time-slice
+@pytest.mark.parametrize("nranks", [2, 5, 8])
+def test_row_sharded_filter_ranks_share_one_gpu(nranks):
+    """The N > 1 CUDA path where only ONE GPU is leased: the ranks share cuda:0, their persistent kernels time-slice
     on the device and exchange the statistics through each other's mailboxes (CUDA IPC).  Same checks as the
-    multi-GPU run: bit-identical replicas, 1e-9 against the unsharded oracle, one collectively chosen kernel."""
-    r = _torchrun(2, 29513, "--same-device", "--quick", env={"PSMF_SPIN_TIMEOUT_MS": "60000"})
+    multi-GPU run: bit-identical replicas, 1e-9 against the unsharded oracle, one collectively chosen kernel.
+    (5 and 8 ranks: a miscompiled gather over more than one peer went unnoticed with 2.)"""
+    r = _torchrun(nranks, 29513 + nranks, "--same-device", "--quick", env={"PSMF_SPIN_TIMEOUT_MS": "60000"})
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("OK") >= 6 and "FAIL" not in r.stdout
+    assert r.stdout.count(" OK") >= 3 * nranks and "FAIL" not in r.stdout
+
+
+@pytest.mark.gpu
+def test_gather_ranks_unit():
+    """gather_ranks (the rank-ordered, concurrently polled sum of one statistics entry over the GPUs) in isolation: every
+    world size 2..8, first / last rank, with and without a local tagged cell, peers arriving one after the other."""
+    import shutil
+    import tempfile
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "gather_test")
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-I", os.path.join(ROOT, "rpsmf_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "cuda", "gather_test.cu"), "-o", exe], check=True, timeout=600)
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.count(": ok") == 28 and "FAIL" not in r.stdout, r.stdout[-2000:]
 
 
 @pytest.mark.gpu
