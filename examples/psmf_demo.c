@@ -109,7 +109,7 @@ int main(int argc, char** argv) {
     double xT[PSMF_MAX_RANK];
     CK_CUDA(cudaMemcpy(xT, dX + (T - 1) * r, sizeof(double) * r, cudaMemcpyDeviceToHost));
     printf("psmf_b200 v%d: d=%lld r=%d T=%lld  kernel=%s  %d CTAs x %d threads  first_bad_step=%lld\nx_T =",
-           psmf_version(), (long long)d, r, (long long)T, kernel == 2 ? "tma" : "direct", ctas, threads, (long long)bad);
+           psmf_version(), (long long)d, r, (long long)T, kernel == PSMF_KERNEL_STREAM ? "tma" : (kernel == PSMF_KERNEL_BATCH ? "batch" : "direct"), ctas, threads, (long long)bad);
     for (int j = 0; j < r; ++j) printf(" %.6f", xT[j]);
     printf("\n");
     CK_PSMF(h, psmf_destroy(h));

@@ -236,9 +236,9 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     e->threads = shp.threads;
     e->cooperative = cps > 1;
 
-    // ---- TMA-staged kernel: slots of V2_TS tiles + y/m slices, residual buffer behind them ----
+    // ---- TMA-staged kernel: slots of v2_ts(R, esize) tiles, residual buffer behind them ----
     if ((cfg->kernel == 0 || cfg->kernel == 2) && cfg->exchange == PSMF_XCHG_NVLINK && e->d % 16 == 0 && e->S == 1 && sms >= 2) {
-        const int TS = V2_TS;
+        const int TS = v2_ts(e->R, (int)e->esize);
         auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
         const size_t slot = r128((size_t)TS * e->R * TILE * e->esize);     // psmf_stream.cuh SlotLayout: one chunk of C
         // data CTAs (one per SM) + one control CTA, all co-resident (cooperative launch)

@@ -41,7 +41,13 @@ constexpr int V3_PF = 4;        // resident batch kernel: tiles per warp whose y
 // resident batch kernel: CTAs per SM the register budget is sized for (shared memory permitting)
 __host__ __device__ constexpr int batch_min_ctas(int R, int NW) { return NW >= 8 ? 2 : (R <= 8 ? 5 : (R <= 12 ? 4 : 3)); }
 constexpr int V2_CWARPS = 14;   // TMA-staged kernel: pass warps (+1 reduce warp, +1 producer warp)
-constexpr int V2_TS = 4;        // TMA-staged kernel: tiles per shared-memory chunk slot
+// TMA-staged kernel: tiles per shared-memory chunk slot.  The single-thread bulk-copy loop costs ~0.6 us per iteration
+// whatever the chunk size (scratch/bulkbench.cu), so a chunk must carry ~16 KB to sustain the HBM rate: 4 tiles at
+// r = 16 / fp64, 8 at fp32 or r = 8, at most 16.
+__host__ __device__ constexpr int v2_ts(int R, int esize) {
+    const int want = 16384 / (R * TILE * esize);
+    return want < 4 ? 4 : (want > 16 ? 16 : want);
+}
 constexpr int MAXW = 12;        // max warps that write per-warp partial statistics in any kernel
 
 __host__ __device__ constexpr int ngram(int R) { return R * (R + 1) / 2; }

@@ -55,7 +55,7 @@ __host__ __device__ constexpr int s_threads() { return (V2_CWARPS + 2) * 32; }
 __host__ __device__ constexpr size_t round128(size_t x) { return (x + 127) / 128 * 128; }
 template <int R, typename T>
 struct SlotLayout {
-    static constexpr int TS = V2_TS;
+    static constexpr int TS = v2_ts(R, (int)sizeof(T));
     static constexpr size_t TILE_BYTES = (size_t)R * TILE * sizeof(T);
     static constexpr size_t SLOT = round128(TS * TILE_BYTES);     // a slot holds one chunk of C, nothing else
 };

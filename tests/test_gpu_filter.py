@@ -190,11 +190,64 @@ def test_run_to_run_determinism():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[3]["C"], b[3]["C"])
 
 
+def _workload_L_on_device(T, dtype, nan_encoded=False):
+    """Workload L of bench.py (d = 1M, r = 16, rPSMF, 20 % missing) generated on the device by the bench generator."""
+    import os
+    import sys
+    torch = _torch()
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench_data as bd
+    d, r = 1_000_000, 16
+    Y, M, C0, x0 = bd.make_series(torch, torch.device("cuda", 0), d, 0, d, r, T, dtype, nan_encoded=nan_encoded)
+    return d, r, Y, M, C0, x0, bd.init_state(r)
+
+
+@pytest.mark.parametrize("dtype,T,tol", [("f64", 600, TOL), ("f32", 300, 1e-4)])
+def test_full_size_workload_L_long_horizon(dtype, T, tol):
+    """BASELINE.json's headline shape over HUNDREDS of steps (north_star: "over the full sequence"): lambda grows by d per
+    step (to 6e8), rho and Q are multiplied by omega every step -- any drift of the pipelined statistics would show.
+    The pipelined kernel, in several launches, against the C/OpenMP oracle (itself pinned against the numpy oracle in the
+    CPU suite) at every step of x_t and at the end for C, P, V, rho, lambda; fp32 storage against the oracle on
+    fp32-rounded inputs at 1e-4.  Size-independent properties: never-observed rows keep their C row bit-exactly."""
+    from oracle import psmf_oracle_c as pc
+    if not pc.available():
+        pytest.skip("oracle/libpsmf_oracle.so not built (python -c 'import __graft_entry__ as g; g.build()')")
+    torch = _torch()
+    from rpsmf_b200 import FilterEngine
+    pc.use_all_cores()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    d, r, Y, M, C0, x0, init = _workload_L_on_device(T, tdt)
+    dead = torch.tensor([0, 31, 32, 4097, 500_000, d - 1], device="cuda")
+    M[:, dead] = 0
+    Y[:, dead] = 0
+    C0 = C0.to(tdt)
+    eng = FilterEngine(d, r, dtype=tdt, robust=True)
+    eng.set_state(C_=C0, V=init["V"], P=init["P"], x=x0, Q=init["Q"], rho=[init["rho"]], lam=[init["lam"]])
+    Xs = []
+    bounds = [0, 1, 250, T]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        Xs.append(eng.run(Y[a:b], M[a:b], k0=1 + a, want_X=True)["X"])
+        assert eng.status() == -1
+    info = eng.launch_info()
+    assert info["kernel"] == "tma" and info["resident"] is False
+    X = torch.cat(Xs).cpu().numpy()
+    st = eng.get_state()
+    ref = pc.run(C0.double().cpu().numpy(), x0.numpy(), init["P"], init["V"], init["Q"], init["rho"], init["lam"],
+                 Y.double().cpu().numpy(), M.cpu().numpy(), robust=True, cupdate_vt=True)
+    assert ref["bad"] == -1
+    per_step = np.max(np.abs(X - ref["X"]), axis=1) / np.max(np.abs(ref["X"]))
+    assert per_step.max() < tol, (int(per_step.argmax()), float(per_step.max()))
+    C = st["C"].double().cpu().numpy()
+    assert relerr(C, ref["C"]) < tol
+    assert relerr(st["P"].cpu().numpy(), ref["P"]) < tol and relerr(st["V"].cpu().numpy(), ref["V"]) < tol
+    assert relerr(st["rho"].cpu().numpy(), ref["rho"]) < tol and relerr(st["lam"].cpu().numpy(), ref["lam"]) < 1e-12
+    dd = dead.cpu().numpy()
+    assert np.array_equal(C[dd], C0.double().cpu().numpy()[dd])
+    eng.close()
+
+
 def test_full_size_workload_L():
-    """BASELINE.json's headline shape (d = 1M, r = 16, rPSMF, 20 % missing) on a short prefix: the pipelined
-    kernel against the C/OpenMP oracle (itself pinned against the numpy oracle in the CPU suite), plus the
-    size-independent properties: a row that is never observed (y zero-filled) keeps its C row bit-exactly,
-    and two runs are bit-identical."""
+    """The headline shape on a short prefix with host-generated data: run-to-run bit-identity and both mask encodings."""
     from oracle import psmf_oracle_c as pc
     if not pc.available():
         pytest.skip("oracle/libpsmf_oracle.so not built (python -c 'import __graft_entry__ as g; g.build()')")
@@ -216,6 +269,10 @@ def test_full_size_workload_L():
     assert np.array_equal(a[3]["C"][dead], C0[dead])
     b = _engine_run(d, r, Y, M, C0, x0, init, True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[3]["C"], b[3]["C"])
+    Yn = Y.copy()
+    Yn[M == 0] = np.nan
+    c = _engine_run(d, r, Yn, None, C0, x0, init, True, nan_mask=True)      # NaN-encoded mask: the same bits
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[3]["C"], c[3]["C"])
 
 
 @pytest.mark.parametrize("d,kernel", [(2_000_000, "tma"), (3_000_000, "direct")])

@@ -1,6 +1,8 @@
 """The experiment driver end to end on the GPU (default fit = the CUDA model functions) against the same driver
 with the oracle as the fit.  Runs last (file name) so that a problem here cannot hide the parity tests under -x."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -25,3 +27,26 @@ def test_experiment_driver_gpu_vs_oracle(method):
         assert np.allclose(a["results"][k], b["results"][k], rtol=1e-9, atol=0)
     assert np.allclose(a["results"]["inside_sig"], b["results"]["inside_sig"], atol=2e-3)
     assert all(t > 0 for t in a["results"]["runtime"])
+
+
+def test_c_demo_runs_on_the_gpu():
+    """examples/psmf_demo.c -- a plain-C caller of the ABI -- compiled, linked AND executed."""
+    import shutil
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    cuda = "/usr/local/cuda"
+    if not gcc or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc / CUDA headers not available")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "psmf_demo")
+        subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(root, "examples", "psmf_demo.c"), "-o", exe, "-L", os.path.join(root, "rpsmf_b200"), "-lpsmf_b200",
+                        "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", "-Wl,-rpath," + os.path.join(root, "rpsmf_b200")], check=True)
+        for args, kernel in ((["40000", "16", "60"], "tma"), (["300", "8", "80"], "batch")):
+            r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+            assert "kernel=" + kernel in r.stdout and "first_bad_step=-1" in r.stdout, r.stdout
+            xs = [float(v) for v in r.stdout.strip().splitlines()[-1].split()[2:]]
+            assert len(xs) == int(args[1]) and all(np.isfinite(xs))
