@@ -256,7 +256,7 @@ def bind_to_gpu_numa_node(torch, index):
             bus = bus[4:]                                          # 00000000:1B:00.0 -> 0000:1b:00.0
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
         if node < 0:
-            return None
+            return "default placement (the kernel reports no NUMA node for %s)" % bus
         cpus = []
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             a, _, b = part.partition("-")
@@ -265,9 +265,9 @@ def bind_to_gpu_numa_node(torch, index):
         if allowed:
             os.sched_setaffinity(0, allowed)
             return "NUMA node %d (%d cores)" % (node, len(allowed))
-    except Exception:
-        pass
-    return None
+        return "default placement (no allowed core on NUMA node %d)" % node
+    except Exception as ex:
+        return "default placement (%s: %s)" % (type(ex).__name__, str(ex)[:80])
 
 
 def _barrier(ctx):

@@ -53,6 +53,10 @@ typedef struct psmf_engine* psmf_handle;
 #define PSMF_NAN_MASK      64  /* missing entries of Y are NaN (the raw data form, rPSMF.py:160-164) and io->M must be NULL:
                                * m = !isnan(y), y := 0 where missing (== rPSMF.py:198-202 done on the fly; no mask stream) */
 
+#define PSMF_RHO_VECTOR   128  /* R is diagonal but NOT uniform (psmf.py:144-152 takes the Woodbury branch for any diagonal R; the
+                               * flat functions accept any (d, d) R): `rho` of psmf_set_state / psmf_get_state is then
+                               * (n_series, d) = diag(R).  One GPU, direct-load kernel.                                */
+
 /* dynamics f_theta(x, k) of the predict half (psmf.py:104-115) */
 #define PSMF_DYN_IDENTITY 0    /* RandomWalk, nonlinearities.py:42-56; Impute scripts */
 #define PSMF_DYN_COS      1    /* cos(2 pi theta k + x), synthetic_psmf.py:105-106 */
@@ -151,7 +155,7 @@ int  psmf_version(void);
 
 /* state round trip (sweep carry-over: psmf.py:75-83, rPSMF.py:75-79).  Any pointer may be NULL = leave /
  * skip.  C is (n_series, d, r) row-major in the engine dtype; V, P, Q are (n_series, r, r) row-major
- * float64; x, theta (n_series, r); rho, lambda (n_series) float64.                                   */
+ * float64; x, theta (n_series, r); rho, lambda (n_series) float64 (PSMF_RHO_VECTOR: rho is (n_series, d)). */
 int  psmf_set_state(psmf_handle h, const void* C, const double* V, const double* P, const double* x,
                     const double* Q, const double* rho, const double* lambda, const double* theta, void* stream);
 int  psmf_get_state(psmf_handle h, void* C, double* V, double* P, double* x,

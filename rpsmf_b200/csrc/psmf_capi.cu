@@ -29,6 +29,14 @@ static const shape_fn SHAPE_S[MAXR + 1] = {
     nullptr,          shape_stream_r1,  shape_stream_r2,  shape_stream_r3,  shape_stream_r4,  shape_stream_r5,
     shape_stream_r6,  shape_stream_r7,  shape_stream_r8,  shape_stream_r9,  shape_stream_r10, shape_stream_r11,
     shape_stream_r12, shape_stream_r13, shape_stream_r14, shape_stream_r15, shape_stream_r16};
+static const launch_fn LAUNCH_V[MAXR + 1] = {
+    nullptr,            launch_filterv_r1,  launch_filterv_r2,  launch_filterv_r3,  launch_filterv_r4,  launch_filterv_r5,
+    launch_filterv_r6,  launch_filterv_r7,  launch_filterv_r8,  launch_filterv_r9,  launch_filterv_r10, launch_filterv_r11,
+    launch_filterv_r12, launch_filterv_r13, launch_filterv_r14, launch_filterv_r15, launch_filterv_r16};
+static const shape_fn SHAPE_V[MAXR + 1] = {
+    nullptr,           shape_filterv_r1,  shape_filterv_r2,  shape_filterv_r3,  shape_filterv_r4,  shape_filterv_r5,
+    shape_filterv_r6,  shape_filterv_r7,  shape_filterv_r8,  shape_filterv_r9,  shape_filterv_r10, shape_filterv_r11,
+    shape_filterv_r12, shape_filterv_r13, shape_filterv_r14, shape_filterv_r15, shape_filterv_r16};
 static const launch_fn LAUNCH_B[MAXR + 1] = {
     nullptr,          launch_batch_r1,  launch_batch_r2,  launch_batch_r3,  launch_batch_r4,  launch_batch_r5,
     launch_batch_r6,  launch_batch_r7,  launch_batch_r8,  launch_batch_r9,  launch_batch_r10, launch_batch_r11,
@@ -59,6 +67,36 @@ __global__ void pack_C(const T* __restrict__ src, T* __restrict__ dst, int64_t d
         dst[idx] = row < d ? src[(s * d + row) * R + j] : (T)0;
     }
 }
+// F_RHO_VECTOR: caller's diag(R) (n_series, d) -> padded copy (whole tiles, 1.0 in the padding) + its mean per series;
+// the state scalar rho becomes the scale (1.0)
+__global__ void rho_pack(const double* __restrict__ src, double* __restrict__ dst, double* __restrict__ mean, double* __restrict__ state,
+                         int64_t d, int64_t ld, int R) {
+    __shared__ double red[256];
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < ld; i += blockDim.x) {
+        const double v = i < d ? src[(int64_t)s * d + i] : 1.0;
+        dst[(int64_t)s * ld + i] = v;
+        acc += i < d ? v : 0.0;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        mean[s] = red[0] / (double)d;
+        state[(int64_t)s * st_size(R) + st_rho(R)] = 1.0;
+    }
+}
+__global__ void rho_unpack(const double* __restrict__ src, const double* __restrict__ state, double* __restrict__ dst, int64_t d, int64_t ld, int R) {
+    const int s = blockIdx.y;
+    const double scale = state[(int64_t)s * st_size(R) + st_rho(R)];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d; i += (int64_t)gridDim.x * blockDim.x)
+        dst[(int64_t)s * d + i] = scale * src[(int64_t)s * ld + i];
+}
+
 template <typename T>
 __global__ void unpack_C(const T* __restrict__ src, T* __restrict__ dst, int64_t d, int R, int64_t ntiles, int64_t total) {
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -103,6 +141,8 @@ struct psmf_engine {
     double* eval_part = nullptr;       // [S][cps][NEVAL] per-CTA evaluation sums of a launch
     double* stats_ext = nullptr;       // PSMF_XCHG_EXTERNAL: statistics of one step / residuals between the two launches
     double* e_ext = nullptr;
+    double* rho_vec = nullptr;         // PSMF_RHO_VECTOR: caller's diag(R), (S, ntiles * 32) padded, and its mean per series
+    double* rho_mean = nullptr;
     double* lin = nullptr;             // PSMF_DYN_LINEAR: A (R * R) then c (R)
     bool lin_set = false, lin_has_c = false;
     double* tool_buf = nullptr;        // scratch of psmf_eval_full / psmf_predict
@@ -154,6 +194,8 @@ static void free_engine(psmf_engine* e) {
     cudaFree(e->stats_ext);
     cudaFree(e->e_ext);
     cudaFree(e->lin);
+    cudaFree(e->rho_vec);
+    cudaFree(e->rho_mean);
     cudaFree(e->tool_buf);
     for (int i = 0; i < PSMF_MAX_PEERS; ++i)
         if (e->peer_mbox[i] && i != e->cfg.rank) cudaIpcCloseMemHandle(e->peer_mbox[i]);
@@ -174,6 +216,9 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     if (cfg->kernel < 0 || cfg->kernel > 3) return fail(nullptr, PSMF_E_INVALID, "kernel must be PSMF_KERNEL_AUTO / DIRECT / STREAM / BATCH");
     if (cfg->exchange != PSMF_XCHG_NVLINK && cfg->exchange != PSMF_XCHG_EXTERNAL)
         return fail(nullptr, PSMF_E_INVALID, "exchange must be PSMF_XCHG_NVLINK or PSMF_XCHG_EXTERNAL");
+    if ((cfg->flags & PSMF_RHO_VECTOR) && (cfg->world_size > 1 || cfg->kernel == 2 || cfg->kernel == 3))
+        return fail(nullptr, PSMF_E_INVALID, "PSMF_RHO_VECTOR (non-uniform diagonal R) runs on the direct-load kernel of one GPU: "
+                                             "world_size 1, kernel AUTO or DIRECT");
     if (cfg->exchange == PSMF_XCHG_EXTERNAL && cfg->n_series > 1)
         return fail(nullptr, PSMF_E_INVALID, "PSMF_XCHG_EXTERNAL shards ONE series by rows (n_series must be 1)");
     if (cfg->world_size < 1 || cfg->world_size > PSMF_MAX_PEERS || cfg->rank < 0 || cfg->rank >= cfg->world_size)
@@ -220,7 +265,7 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     for (;;) {
         const int64_t tiles_per = (e->ntiles + cps - 1) / cps + 1;
         e->dyn_smem = stage_bytes + (size_t)tiles_per * TILE * sizeof(double);
-        ce = SHAPE[e->R](cfg->dtype, e->dyn_smem, &shp);
+        ce = ((cfg->flags & PSMF_RHO_VECTOR) ? SHAPE_V : SHAPE)[e->R](cfg->dtype, e->dyn_smem, &shp);
         if (ce == cudaSuccess && shp.max_ctas_per_sm >= 1) break;
         cudaGetLastError();
         // residual buffer does not fit: use more CTAs if allowed
@@ -237,7 +282,8 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     e->cooperative = cps > 1;
 
     // ---- TMA-staged kernel: slots of v2_ts(R, esize) tiles, residual buffer behind them ----
-    if ((cfg->kernel == 0 || cfg->kernel == 2) && cfg->exchange == PSMF_XCHG_NVLINK && e->d % 16 == 0 && e->S == 1 && sms >= 2) {
+    if ((cfg->kernel == 0 || cfg->kernel == 2) && !(cfg->flags & PSMF_RHO_VECTOR) && cfg->exchange == PSMF_XCHG_NVLINK &&
+        e->d % 16 == 0 && e->S == 1 && sms >= 2) {
         const int TS = v2_ts(e->R, (int)e->esize);
         auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
         const size_t slot = r128((size_t)TS * e->R * TILE * e->esize);     // psmf_stream.cuh SlotLayout: one chunk of C
@@ -285,7 +331,7 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
         return fail(nullptr, PSMF_E_INVALID, "TMA-staged kernel not available for this shape (needs d % 16 == 0, one series, and room for a ring of 5 chunk slots)");
     }
     // ---- resident batch kernel: one CTA per series, the whole dictionary of a series in shared memory ----
-    if ((cfg->kernel == 0 || cfg->kernel == 3) && cfg->world_size == 1) {
+    if ((cfg->kernel == 0 || cfg->kernel == 3) && cfg->world_size == 1 && !(cfg->flags & PSMF_RHO_VECTOR)) {
         e->batch_nw8 = e->ntiles >= 8 && e->S <= 2 * sms;       // few series: more warps per series; many: more series per SM
         e->dyn_smem3 = batch_dyn(e->ntiles, e->R, e->esize, false);
         LaunchShape sb;
@@ -302,7 +348,8 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
     }
 
     const size_t cbytes = (size_t)e->S * e->ntiles * TILE * e->R * e->esize;
-    const int nsp = (ngram(e->R) + 2 * e->R + 5 + 7) / 8 * 8;      // >= nstat_pad(R): pipelined statistics (nstat2_pad)
+    // >= nstat_pad(R): pipelined statistics (nstat2_pad), or the longer vector of a non-uniform diagonal R
+    const int nsp = (cfg->flags & PSMF_RHO_VECTOR) ? nstat_v_pad(e->R) : (ngram(e->R) + 2 * e->R + 5 + 7) / 8 * 8;
 #define CKC(call)                                                                                            \
     do {                                                                                                     \
         cudaError_t e__ = (call);                                                                            \
@@ -339,6 +386,10 @@ extern "C" int psmf_create(psmf_handle* out, const psmf_config* cfg) {
         CKC(cudaMemset(e->e_ext, 0, (size_t)(e->ntiles + 1) * TILE * sizeof(double)));
     }
     CKC(cudaMalloc(&e->eval_part, (size_t)e->S * (e->cps > 1 ? e->cps : 1) * NEVAL * sizeof(double)));
+    if (cfg->flags & PSMF_RHO_VECTOR) {
+        CKC(cudaMalloc(&e->rho_vec, (size_t)e->S * e->ntiles * TILE * sizeof(double)));
+        CKC(cudaMalloc(&e->rho_mean, (size_t)e->S * sizeof(double)));
+    }
     CKC(cudaMalloc(&e->lin, (size_t)(e->R * e->R + e->R) * sizeof(double)));
     CKC(cudaMemset(e->lin, 0, (size_t)(e->R * e->R + e->R) * sizeof(double)));
 #undef CKC
@@ -387,7 +438,17 @@ static int state_io(psmf_engine* h, bool set, void* C, double* V, double* P, dou
     if ((rc = copy_small(h, set, V, st_V(R), R * R, st))) return rc;
     if ((rc = copy_small(h, set, Q, st_Q(R), R * R, st))) return rc;
     if ((rc = copy_small(h, set, theta, st_theta(R), R, st))) return rc;
-    if ((rc = copy_small(h, set, rho, st_rho(R), 1, st))) return rc;
+    if (rho && (h->cfg.flags & PSMF_RHO_VECTOR)) {
+        // diag(R) as a vector per series: the engine keeps the caller's vector and a scalar scale (R <- omega R, rPSMF.py:134)
+        const int64_t ld = h->ntiles * TILE;
+        if (set) {
+            rho_pack<<<h->S, 256, 0, st>>>(rho, h->rho_vec, h->rho_mean, h->state, h->d, ld, R);
+        } else {
+            dim3 grid((unsigned)((h->d + 255) / 256 > 1024 ? 1024 : (h->d + 255) / 256), (unsigned)h->S);
+            rho_unpack<<<grid, 256, 0, st>>>(h->rho_vec, h->state, rho, h->d, ld, R);
+        }
+        CK(h, cudaGetLastError());
+    } else if ((rc = copy_small(h, set, rho, st_rho(R), 1, st))) return rc;
     if ((rc = copy_small(h, set, lambda, st_lam(R), 1, st))) return rc;
     return PSMF_OK;
 }
@@ -459,6 +520,7 @@ static int run_impl(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k
     p.phase = phase;
     p.stats_ext = h->stats_ext; p.e_ext = h->e_ext;
     p.lin_A = h->lin; p.lin_c = h->lin_has_c ? h->lin + h->R * h->R : nullptr;
+    p.rho_vec = h->rho_vec; p.rho_sst = h->ntiles * TILE; p.rho_mean = h->rho_mean;
     if (eval) {
         p.Yorig = io->Yorig; p.E = io->E; p.lde = io->lde; p.esst = io->e_series_stride; p.sig = io->sig;
         p.eval_part = h->eval_part;
@@ -521,7 +583,8 @@ static int run_impl(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k
         // streaming from HBM: 12 of the 14 pass warps (3 per scheduler; a multiple of the 4 tiles of a chunk) keep up
         // with the ring and leave issue slots to the producer -- measured optimum at r = 16 under the power cap;
         // resident in shared memory: every warp helps
-        p.npw = h->resident2 ? V2_CWARPS : 12;
+        // fp32 storage halves the bytes per tile: the pass is bound by the fp64 pipe, not by the ring -> all 14 warps
+        p.npw = (h->resident2 || h->cfg.dtype == PSMF_F32) ? V2_CWARPS : 12;
 #ifdef PSMF_DEBUG
         if (const char* ev = getenv("PSMF_NPW")) { const int v = atoi(ev); if (v >= 1 && v <= V2_CWARPS) p.npw = v; }
 #endif
@@ -535,13 +598,13 @@ static int run_impl(psmf_handle h, const psmf_io* io, int64_t n_steps, int64_t k
             const int64_t tiles_per = (h->ntiles + h->cps - 1) / h->cps + 1;
             dyn1 += (size_t)tiles_per * TILE * 17 + 16;
             LaunchShape sh1;
-            if (SHAPE[h->R](h->cfg.dtype, dyn1, &sh1) != cudaSuccess || sh1.max_ctas_per_sm < 1 ||
+            if (((h->cfg.flags & PSMF_RHO_VECTOR) ? SHAPE_V : SHAPE)[h->R](h->cfg.dtype, dyn1, &sh1) != cudaSuccess || sh1.max_ctas_per_sm < 1 ||
                 (h->cooperative && h->cps > h->num_sms * sh1.max_ctas_per_sm)) {
                 cudaGetLastError();
                 return fail(h, PSMF_E_NOMEM, "no shared memory left for the evaluation buffers at this d / grid");
             }
         }
-        CK(h, LAUNCH[h->R](p, h->cfg.dtype, h->S * h->cps, dyn1, st, h->cooperative));
+        CK(h, ((h->cfg.flags & PSMF_RHO_VECTOR) ? LAUNCH_V : LAUNCH)[h->R](p, h->cfg.dtype, h->S * h->cps, dyn1, st, h->cooperative));
         h->last_kernel = 1;
         h->last_dyn = dyn1;
     }

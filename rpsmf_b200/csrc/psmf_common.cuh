@@ -20,7 +20,8 @@ constexpr int MAXR = 16;
 constexpr int MAX_PEERS = 8;
 
 // flags (mirror include/psmf_b200.h)
-constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16, F_LL_STUDENT = 32, F_NAN_MASK = 64;
+constexpr int F_ROBUST = 1, F_SIMPLIFIED = 2, F_CUPDATE_VT = 4, F_FIXED_LAMBDA = 16, F_LL_STUDENT = 32, F_NAN_MASK = 64,
+              F_RHO_VECTOR = 128;
 constexpr int DYN_IDENTITY = 0, DYN_COS = 1, DYN_LINEAR = 2, DYN_EXTERNAL = 3;
 constexpr int NEVAL = 4;     // fused evaluation record (include/psmf_b200.h PSMF_EVAL_*)
 // debug-only flag bits (env PSMF_DEBUG_FLAGS; results are WRONG with them): compiled in only with -DPSMF_DEBUG,
@@ -57,6 +58,14 @@ __host__ __device__ constexpr int nstat_pad(int R) { return (nstat(R) + 7) / 8 *
 // pipelined kernel: packed upper triangle of A0, u (R), h0 (R), kappa, psi, gamma, q0, n_obs
 __host__ __device__ constexpr int nstat2(int R) { return ngram(R) + 2 * R + 5; }
 __host__ __device__ constexpr int nstat2_pad(int R) { return (nstat2(R) + 7) / 8 * 8; }
+// non-uniform diagonal R (F_RHO_VECTOR): w_i = 1 / (rho_i + a) differs per row, so the weighted Gram no longer follows
+// from the unweighted one -- both are reduced:  [G = sum m w c c' | b = sum m w e c | s q1 q0 n_obs | G0 = sum m c c' |
+// bu = sum m e c | n_rho = sum m rho]
+__host__ __device__ constexpr int nstat_v(int R) { return 2 * ngram(R) + 2 * R + 5; }
+__host__ __device__ constexpr int nstat_v_pad(int R) { return (nstat_v(R) + 7) / 8 * 8; }
+__host__ __device__ constexpr int sv_G0(int R) { return ngram(R) + R + 4; }
+__host__ __device__ constexpr int sv_bu(int R) { return 2 * ngram(R) + R + 4; }
+__host__ __device__ constexpr int sv_nrho(int R) { return 2 * ngram(R) + 2 * R + 4; }
 // packed index of Gram entry (j, j) in row-major upper-triangular order
 __host__ __device__ constexpr int gram_off(int R, int j) { return j * R - j * (j - 1) / 2; }
 // tagged 16-byte cells behind KParams.gparams: [2][2 MAXR] parameter sets, then [2][nstat2_pad(MAXR)] reduced totals
@@ -121,6 +130,9 @@ struct KParams {
     int32_t phase;
     double* stats_ext;        // nstat_pad(R) doubles
     double* e_ext;            // d doubles
+    const double* rho_vec;    // F_RHO_VECTOR: diag(R) as set by the caller, (n_series, rho_sst) padded to whole tiles; the state
+    int64_t rho_sst;          // scalar `rho` is then the accumulated scale prod omega_k (rPSMF.py:134 multiplies all of R)
+    const double* rho_mean;   // F_RHO_VECTOR: mean of the caller's diag(R) per series (tr(R)/d of the simplified step)
     const double* lin_A;      // DYN_LINEAR: (r, r) row-major A and (r) offset c (x_bar = A x + c, F = A), device pointers
     const double* lin_c;
     unsigned long long spin_ns; // a wait (tagged cell, mbarrier, grid barrier, NVLink mailbox) that makes no progress for
@@ -157,6 +169,8 @@ typedef cudaError_t (*shape_fn)(int dtype, size_t dyn_smem, LaunchShape*);
     namespace psmf {                                                                                        \
     cudaError_t launch_filter_r##n(const KParams&, int, int, size_t, cudaStream_t, bool);                   \
     cudaError_t shape_filter_r##n(int, size_t, LaunchShape*);                                               \
+    cudaError_t launch_filterv_r##n(const KParams&, int, int, size_t, cudaStream_t, bool);                  \
+    cudaError_t shape_filterv_r##n(int, size_t, LaunchShape*);                                              \
     cudaError_t launch_stream_r##n(const KParams&, int, int, size_t, cudaStream_t, bool);                   \
     cudaError_t shape_stream_r##n(int, size_t, LaunchShape*);                                               \
     cudaError_t launch_batch_r##n(const KParams&, int, int, size_t, cudaStream_t, bool);                    \

@@ -20,6 +20,7 @@
 // Every CTA (and every GPU) derives the small state from bit-identical reduced statistics, so the
 // replicated r x r state never diverges.
 #pragma once
+#include <type_traits>
 #include "psmf_common.cuh"
 
 namespace psmf {
@@ -312,6 +313,88 @@ __device__ __forceinline__ void acc_writeout(TileAcc<R>& A, double* __restrict__
         if (base + i < lim) red[ngram(R) + base + i] = A.v[i];
 }
 
+// ---- non-uniform diagonal R (F_RHO_VECTOR; psmf.py:144-152 takes the Woodbury branch for ANY diagonal R) -------------
+// Per-row weights w_i = 1 / (rho_i + a): the weighted Gram G (for K) and the unweighted G0 (for eta = tr(M R M + C Pbar C')
+// / d, rPSMF.py:108) are both accumulated, as fp64 DMMAs on the same fragments; sum m e c (theta gradient) rides along as
+// plain FMAs on the element a lane holds anyway, like [u | h0] of the pipelined kernel.
+template <int R>
+struct TileAccV : TileAcc<R> {
+    double h00[2], h01[2], h11[2];   // fragments of sum_i m_i w_i c_i c_i'
+    double u0, u1;                   // partial sums of sum m e c for column lane/4 (u0) and 8 + lane/4 (u1)
+    double nrho;                     // per-lane sum m rho
+    __device__ __forceinline__ void zero_v() {
+        this->zero();
+        h00[0] = h00[1] = h01[0] = h01[1] = h11[0] = h11[1] = u0 = u1 = nrho = 0.0;
+    }
+};
+template <int R, typename TS>
+__device__ __forceinline__ void tile_gram_v(TileAccV<R>& A, const TS* __restrict__ tile, unsigned mbits, double wm, double me, int lane) {
+    const int kk = lane & 3, mm = lane >> 2;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const int row = 4 * s + kk;
+        const bool mrow = (mbits >> row) & 1u;
+        const int pos = row ^ (mm << 2);
+        const double wr = __shfl_sync(FULL, wm, row), er = __shfl_sync(FULL, me, row);     // m w and m e of the row
+        const double a0 = (mm < R) ? (double)tile[mm * 32 + pos] : 0.0;
+        dmma884(A.g00, a0, mrow ? a0 : 0.0);
+        dmma884(A.h00, a0, a0 * wr);
+        A.u0 = fma(a0, er, A.u0);
+        if constexpr (R > 8) {
+            const double a1 = (8 + mm < R) ? (double)tile[(8 + mm) * 32 + pos] : 0.0;
+            const double b1 = mrow ? a1 : 0.0, c1 = a1 * wr;
+            dmma884(A.g01, a0, b1);
+            dmma884(A.g11, a1, b1);
+            dmma884(A.h01, a0, c1);
+            dmma884(A.h11, a1, c1);
+            A.u1 = fma(a1, er, A.u1);
+        }
+    }
+}
+template <int R>
+__device__ __forceinline__ void acc_writeout_v(TileAccV<R>& A, double* __restrict__ red, int lane) {
+    const int kk = lane & 3, mm = lane >> 2;
+    double* g0 = red + sv_G0(R);
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        const int n = 2 * kk + x;
+        if (mm <= n && n < R) {
+            red[gram_off(R, mm) + (n - mm)] = A.h00[x];
+            g0[gram_off(R, mm) + (n - mm)] = A.g00[x];
+        }
+        if constexpr (R > 8) {
+            if (8 + n < R) {
+                red[gram_off(R, mm) + (8 + n - mm)] = A.h01[x];
+                g0[gram_off(R, mm) + (8 + n - mm)] = A.g01[x];
+            }
+            if (mm <= n && 8 + n < R) {
+                red[gram_off(R, 8 + mm) + (n - mm)] = A.h11[x];
+                g0[gram_off(R, 8 + mm) + (n - mm)] = A.g11[x];
+            }
+        }
+    }
+    constexpr int NV = R + 4;
+    int base = 0, lim = NV;
+    bfly<NV, 16, NV>(A.v, lane, base, lim);
+    constexpr int NF = bfly_final(NV);
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+        if (base + i < lim) red[ngram(R) + base + i] = A.v[i];
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {                              // sum over the four row classes kk (fixed order)
+        A.u0 += __shfl_xor_sync(FULL, A.u0, o);
+        if constexpr (R > 8) A.u1 += __shfl_xor_sync(FULL, A.u1, o);
+    }
+    if (kk == 0) {
+        if (mm < R) red[sv_bu(R) + mm] = A.u0;
+        if constexpr (R > 8) {
+            if (8 + mm < R) red[sv_bu(R) + 8 + mm] = A.u1;
+        }
+    }
+    const double nr = warp_allsum(A.nrho);
+    if (lane == 0) red[sv_nrho(R)] = nr;
+}
+
 // x_bar_i = c_i + sum_k A_ik x_k in a FIXED operation order: the pipelined kernel evaluates it in two places (the
 // published x_bar of the data CTAs and the control CTA's own copy) and both must be bit-identical
 template <int R>
@@ -499,12 +582,16 @@ __device__ void gauss_jordan_cta(Smem<R>& sh, int tid) {
 // ---- r x r part of the step (rPSMF.py:102-115,133-135), identical on every CTA; all `nthr` threads ----
 template <int R, int NGJ, int BAR = 0, int GJBAR = 1>
 __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, int warp, int series, int64_t t,
-                             bool writer, int nthr) {
+                             bool writer, int nthr, const double* totv = nullptr) {
     constexpr int NGm = ngram(R);
     constexpr int FIN = R & 1;                      // buffer holding the result of the elimination
     const bool simp = (p.flags & F_SIMPLIFIED) != 0;
     const bool robust = (p.flags & F_ROBUST) != 0;
-    const double* tot = sh.tot;
+    // totv != nullptr: non-uniform diagonal R, statistics in the nstat_v layout (G, b, s, q1, q0, n_obs as usual, then
+    // the unweighted Gram, sum m e c and sum m rho)
+    const bool rhov = totv != nullptr;
+    const double* tot = rhov ? totv : sh.tot;
+    const double* G0p = rhov ? totv + sv_G0(R) : sh.tot;
     if (!simp) {
         for (int idx = tid; idx < R * R; idx += nthr) {
             const int i = idx / R, j = idx % R;
@@ -547,10 +634,10 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
 #pragma unroll
                 for (int i = 0; i < R; i += 2) {
                     const int lo = i < lane ? i : lane, hi = i < lane ? lane : i;
-                    t0 = fma(sh.Pb[i * R + lane], tot[gram_off(R, lo) + hi - lo], t0);
+                    t0 = fma(sh.Pb[i * R + lane], G0p[gram_off(R, lo) + hi - lo], t0);
                     if (i + 1 < R) {
                         const int lo1 = i + 1 < lane ? i + 1 : lane, hi1 = i + 1 < lane ? lane : i + 1;
-                        t1 = fma(sh.Pb[(i + 1) * R + lane], tot[gram_off(R, lo1) + hi1 - lo1], t1);
+                        t1 = fma(sh.Pb[(i + 1) * R + lane], G0p[gram_off(R, lo1) + hi1 - lo1], t1);
                     }
                 }
                 trpg = t0 + t1;
@@ -561,10 +648,11 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         double sSe, eta;
         if (simp) {
             sSe = s;                                                           // synthetic_rpsmf.py:93-98
-            eta = rho;                                                         // synthetic_psmf.py:86-87
+            eta = rhov ? rho * p.rho_mean[series] : rho;                       // tr(R)/d, synthetic_psmf.py:86-87
         } else {
             sSe = s - bkb;                                                     // diff' CPinv diff
-            eta = (rho * nobs + (rho + a) * trpg) / dg;                        // rPSMF.py:108
+            // rPSMF.py:108: trace(M R M + CM Pbar CM') / d; uniform R: sum m c c' = (rho + a) G
+            eta = rhov ? (tot[sv_nrho(R)] + trpg) / dg : (rho * nobs + (rho + a) * trpg) / dg;
         }
         const double omega = robust ? (lam + sSe) / (lam + dg) : 1.0;          // rPSMF.py:105
         const double N = a + eta;                                              // rPSMF.py:109
@@ -576,7 +664,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
                 // d ell_k / d theta = J_theta' d ell_k / d f with f = x_bar, s = f'Vf + eta = N, e = y - M C f
                 // (psmf.py:57-64,167-177; rpsmf.py:62-71,196-200); C'Me = b (rho + a), n = n_obs, q = q1
                 const double vsf = 0.5 * (sh.vx[lane] + sh.vxt[lane]);
-                const double cte = tot[NGm + lane] * (rho + a);
+                const double cte = rhov ? tot[sv_bu(R) + lane] : tot[NGm + lane] * (rho + a);
                 double gf;
                 if ((p.flags & F_LL_STUDENT) != 0) {
                     const double gq = 1.0 + q1 / (lam * N);
@@ -813,12 +901,15 @@ __device__ __forceinline__ void observe(const KParams& p, const T* __restrict__ 
 // owns them; general fallback (any alignment, any d) and the path for small problems / batched series ----
 // p.phase (caller-driven statistics exchange, one step per launch): 1 = pass + grid reduction, statistics -> p.stats_ext
 // and residuals -> p.e_ext; 2 = r x r update from p.stats_ext (all-reduced by the caller) + the rank-1 update of C.
-template <int R, typename T>
+template <int R, typename T, bool RHOV = false>
 __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KParams p) {
-    constexpr int NW = V1_WARPS, NSP = nstat_pad(R), NST = nstat(R);
+    constexpr int NW = V1_WARPS, NSP = RHOV ? nstat_v_pad(R) : nstat_pad(R), NST = RHOV ? nstat_v(R) : nstat(R);
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ Smem<R> sh;
-    __shared__ double red[V1_WARPS * nstat_pad(R)];                            // per-warp partial statistics
+    __shared__ double red[V1_WARPS * NSP];                                     // per-warp partial statistics
+    __shared__ double totv[RHOV ? NSP : 1], partv[RHOV ? NSP : 1];             // non-uniform R: the longer statistics vector
+    double* const part_p = RHOV ? partv : sh.part;
+    double* const tot_p = RHOV ? totv : sh.tot;
     double* stage_all = reinterpret_cast<double*>(dyn_smem);                   // NW staging tiles [R][32] fp64
     double* ebuf = stage_all + NW * R * TILE;
 
@@ -872,8 +963,10 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
         stamp(p, t, 0);
         const double w1 = sh.w1, w0 = sh.w0;
         if (p.phase != 2) {
-            TileAcc<R> acc;
-            acc.zero();
+            typename std::conditional<RHOV, TileAccV<R>, TileAcc<R>>::type acc;
+            if constexpr (RHOV) acc.zero_v(); else acc.zero();
+            const double* __restrict__ rho0 = RHOV ? p.rho_vec + (int64_t)series * p.rho_sst : nullptr;
+            const double rscale = sh.rho, aa = sh.a;
             for (int tile = tb + warp; tile < te; tile += NW) {
                 const int64_t row = (int64_t)tile * TILE + lane;
                 const int rl = (tile - tb) * TILE + lane;
@@ -888,7 +981,13 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
                 observe<T>(p, Yt, Mt, row, inb, yi, mi);
                 if (evalon && t > 0) eval_cover(ev, eb, rl, sh.sc[7], sh.sc[1], sh.sc[2], robust, p.sig);   // step t-1, now that eta exists
                 double e, yh;
-                row_stats<R>(acc, sh, c, ep, inb, mi, yi, w1, w0, e, yh);
+                double wi = w1;
+                if constexpr (RHOV) {
+                    const double rho_i = inb ? __dmul_rn(rscale, rho0[row]) : 1.0;       // R = omega-scale * diag(R0)  (rPSMF.py:134)
+                    wi = 1.0 / (rho_i + aa);                                               // rPSMF.py:92,98,32
+                    acc.nrho += mi ? rho_i : 0.0;
+                }
+                row_stats<R>(acc, sh, c, ep, inb, mi, yi, wi, w0, e, yh);
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     gt[tile_pos(j, lane)] = (T)c[j];
@@ -899,34 +998,36 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
                 if (evalon) eval_row(ev, eb, rl, inb && Et[row] != 0, mi, yh, inb ? (double)Yo_t[row] : 0.0);
                 const unsigned mbits = __ballot_sync(FULL, mi);
                 __syncwarp();
-                tile_gram<R, double>(acc, stage, mbits, lane);
+                if constexpr (RHOV) tile_gram_v<R, double>(acc, stage, mbits, mi ? wi : 0.0, mi ? e : 0.0, lane);
+                else tile_gram<R, double>(acc, stage, mbits, lane);
                 __syncwarp();
             }
-            acc_writeout<R>(acc, red + warp * NSP, w1, lane);
+            if constexpr (RHOV) acc_writeout_v<R>(acc, red + warp * NSP, lane);
+            else acc_writeout<R>(acc, red + warp * NSP, w1, lane);
             stamp(p, t, 1);
             __syncthreads();
             stamp(p, t, 2);
-            if (tid < NST) {                                   // CTA partial: fixed order over the warps
+            for (int e2 = tid; e2 < NST; e2 += blockDim.x) {   // CTA partial: fixed order over the warps
                 double s = 0.0;
 #pragma unroll
-                for (int w = 0; w < NW; ++w) s += red[w * NSP + tid];
-                sh.part[tid] = s;
+                for (int w = 0; w < NW; ++w) s += red[w * NSP + e2];
+                part_p[e2] = s;
             }
-            grid_reduce<NST, NSP>(p, sh.part, sh.tot, tid, lane, warp, t, series, part, blockDim.x);
+            grid_reduce<NST, NSP>(p, part_p, tot_p, tid, lane, warp, t, series, part, blockDim.x);
             stamp(p, t, 5);
         }
         if (p.phase == 1) {
             // statistics of this GPU's rows -> the caller's collective; residuals survive the launch in global memory
             if (writer)
-                for (int e = tid; e < NST; e += blockDim.x) p.stats_ext[e] = sh.tot[e];
+                for (int e = tid; e < NST; e += blockDim.x) p.stats_ext[e] = tot_p[e];
             for (int i = tid; i < nrows; i += blockDim.x) p.e_ext[(int64_t)tb * TILE + i] = ebuf[i];
             return;
         }
         if (p.phase == 2) {
-            for (int e = tid; e < NST; e += blockDim.x) sh.tot[e] = p.stats_ext[e];
+            for (int e = tid; e < NST; e += blockDim.x) tot_p[e] = p.stats_ext[e];
             __syncthreads();
         }
-        small_update<R, GJ_THREADS>(p, sh, tid, lane, warp, series, t, writer, blockDim.x);
+        small_update<R, GJ_THREADS>(p, sh, tid, lane, warp, series, t, writer, blockDim.x, RHOV ? totv : nullptr);
         stamp(p, t, 6);
     }
 

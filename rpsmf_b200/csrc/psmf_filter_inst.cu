@@ -10,9 +10,9 @@
 
 namespace psmf {
 
-template <typename T>
+template <typename T, bool RHOV = false>
 static cudaError_t launch_t(const KParams& p, int grid, size_t dyn, cudaStream_t st, bool coop) {
-    auto kern = psmf_filter_kernel<PSMF_R, T>;
+    auto kern = psmf_filter_kernel<PSMF_R, T, RHOV>;
     constexpr int threads = V1_WARPS * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
@@ -25,9 +25,9 @@ static cudaError_t launch_t(const KParams& p, int grid, size_t dyn, cudaStream_t
     return cudaGetLastError();
 }
 
-template <typename T>
+template <typename T, bool RHOV = false>
 static cudaError_t shape_t(size_t dyn, LaunchShape* out) {
-    auto kern = psmf_filter_kernel<PSMF_R, T>;
+    auto kern = psmf_filter_kernel<PSMF_R, T, RHOV>;
     constexpr int threads = V1_WARPS * 32;
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, kern);
@@ -48,6 +48,14 @@ cudaError_t PSMF_CAT(launch_filter_r, PSMF_R)(const KParams& p, int dtype, int g
 }
 cudaError_t PSMF_CAT(shape_filter_r, PSMF_R)(int dtype, size_t dyn, LaunchShape* out) {
     return dtype == 0 ? shape_t<double>(dyn, out) : shape_t<float>(dyn, out);
+}
+
+// non-uniform diagonal R (F_RHO_VECTOR)
+cudaError_t PSMF_CAT(launch_filterv_r, PSMF_R)(const KParams& p, int dtype, int grid, size_t dyn, cudaStream_t st, bool coop) {
+    return dtype == 0 ? launch_t<double, true>(p, grid, dyn, st, coop) : launch_t<float, true>(p, grid, dyn, st, coop);
+}
+cudaError_t PSMF_CAT(shape_filterv_r, PSMF_R)(int dtype, size_t dyn, LaunchShape* out) {
+    return dtype == 0 ? shape_t<double, true>(dyn, out) : shape_t<float, true>(dyn, out);
 }
 
 }  // namespace psmf

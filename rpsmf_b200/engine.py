@@ -30,7 +30,7 @@ class FilterEngine:
     def __init__(self, d, r, *, n_series=1, dtype=torch.float64, robust=True, simplified=False,
                  c_update_transpose=True, fixed_lambda=False, ll_student=False, dynamics=_capi.DYN_IDENTITY, alpha=1.0,
                  beta=1.0, device=None, d_global=None, world_size=1, rank=0, ctas=0, kernel=0, nan_mask=False,
-                 exchange="nvlink"):
+                 exchange="nvlink", rho_vector=False):
         if not torch.cuda.is_available():
             raise RuntimeError("rpsmf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         if dtype not in (torch.float64, torch.float32):
@@ -46,6 +46,8 @@ class FilterEngine:
         flags |= _capi.FIXED_LAMBDA if fixed_lambda else 0
         flags |= _capi.LL_STUDENT if ll_student else 0
         flags |= _capi.NAN_MASK if nan_mask else 0
+        flags |= _capi.RHO_VECTOR if rho_vector else 0
+        self.rho_vector = bool(rho_vector)
         self.nan_mask = bool(nan_mask)
         if exchange not in ("nvlink", "external"):
             raise ValueError("exchange must be 'nvlink' (in-kernel mailboxes) or 'external' (caller-supplied collective)")
@@ -101,7 +103,8 @@ class FilterEngine:
             return t.reshape(shape)
 
         ts = [prep(C_, (S, d, r), self.dtype), prep(V, (S, r, r), f64), prep(P, (S, r, r), f64), prep(x, (S, r), f64),
-              prep(Q, (S, r, r), f64), prep(rho, (S,), f64), prep(lam, (S,), f64), prep(theta, (S, r), f64)]
+              prep(Q, (S, r, r), f64), prep(rho, (S, d) if self.rho_vector else (S,), f64), prep(lam, (S,), f64),
+              prep(theta, (S, r), f64)]
         ptrs = [C.c_void_p(t.data_ptr()) if t is not None else None for t in ts]
         with torch.cuda.device(self.device):
             self._ck(self._L.psmf_set_state(self._h, *ptrs, self._stream()))
@@ -115,7 +118,7 @@ class FilterEngine:
             C=torch.empty((S, d, r), dtype=self.dtype, device=dev) if want_C else None,
             V=torch.empty((S, r, r), dtype=f64, device=dev), P=torch.empty((S, r, r), dtype=f64, device=dev),
             x=torch.empty((S, r), dtype=f64, device=dev), Q=torch.empty((S, r, r), dtype=f64, device=dev),
-            rho=torch.empty((S,), dtype=f64, device=dev), lam=torch.empty((S,), dtype=f64, device=dev),
+            rho=torch.empty((S, d) if self.rho_vector else (S,), dtype=f64, device=dev), lam=torch.empty((S,), dtype=f64, device=dev),
             theta=torch.empty((S, r), dtype=f64, device=dev))
         order = ("C", "V", "P", "x", "Q", "rho", "lam", "theta")
         ptrs = [C.c_void_p(out[k].data_ptr()) if out[k] is not None else None for k in order]

@@ -22,18 +22,23 @@ from .engine import FilterEngine, ingest, transpose_mask
 
 
 def _uniform_diag(R, d, name):
-    """The CUDA path supports R = rho * I only (every experiment of the reference uses that)."""
+    """diag(R) for the CUDA path: a float when R = rho * I (every experiment of the reference), else the (d,) vector of a
+    non-uniform diagonal R (PSMF_RHO_VECTOR).  Non-diagonal R is rejected -- the reference itself assumes a diagonal
+    (rPSMF.py:91 inverts it entry by entry)."""
     R = np.asarray(R, dtype=np.float64)
     if R.ndim == 0:
         return float(R)
-    if R.shape != (d, d):
+    if R.shape == (d,):
+        dg = R
+    elif R.shape == (d, d):
+        dg = np.diagonal(R)
+        if np.count_nonzero(R - np.diag(dg)) != 0:
+            raise NotImplementedError("%s must be diagonal (the reference itself assumes this, rPSMF.py:91)" % name)
+    else:
         raise ValueError("%s must be (d, d)" % name)
-    dg = np.diagonal(R)
-    if np.count_nonzero(R - np.diag(dg)) != 0:
-        raise NotImplementedError("%s must be diagonal (the reference itself assumes this, rPSMF.py:91)" % name)
-    if not np.all(dg == dg[0]):
-        raise NotImplementedError("%s must be rho * I: non-uniform diagonals are not supported" % name)
-    return float(dg[0])
+    if np.all(dg == dg[0]):
+        return float(dg[0])
+    return np.ascontiguousarray(dg, dtype=np.float64)
 
 
 def _fit(Y, C, X, d, n, r, M, Mmiss, V, Q0, R0, P, lambda0, sig, Iter, YorigInt, Einit, robust, device=None,
@@ -58,15 +63,17 @@ def _fit(Y, C, X, d, n, r, M, Mmiss, V, Q0, R0, P, lambda0, sig, Iter, YorigInt,
     Yo, _ = ingest(YorigInt, dtype=dtype, keep_nan=False, want_mask=False, device=dev.index)
     Et = transpose_mask(Mmiss, device=dev.index)
 
+    rho_vector = np.ndim(rho0) != 0
+    rho_arg = rho0 if rho_vector else [rho0]
     eng = FilterEngine(d, r, dtype=dtype, robust=robust, c_update_transpose=robust, dynamics=_capi.DYN_IDENTITY,
-                       device=dev.index)
+                       device=dev.index, rho_vector=rho_vector)
     InsideBars = 0.0                                                            # Iter = 0: the bounds stay zero
     details = {}
     try:
-        eng.set_state(C_=C, V=V, P=P, x=np.ascontiguousarray(X[:, n - 1]), Q=Q0, rho=[rho0], lam=[lambda0 if robust else 0.0])
+        eng.set_state(C_=C, V=V, P=P, x=np.ascontiguousarray(X[:, n - 1]), Q=Q0, rho=rho_arg, lam=[lambda0 if robust else 0.0])
         for i in range(Iter):
             if robust:
-                eng.set_state(Q=Q0, rho=[rho0], lam=[lambda0])                 # rPSMF.py:77-79
+                eng.set_state(Q=Q0, rho=rho_arg, lam=[lambda0])                # rPSMF.py:77-79
             # x_bar of t = 0 wraps to X[:, n-1] (rPSMF.py:86): that is the engine's carried x.  The evaluation of the
             # one-step predictions (Epred, the 2-sigma coverage) is accumulated inside the filter pass.
             out = eng.run(Yt, Mt, k0=1, want_X=True, want_scal=return_details, want_Yrec=return_details, Yorig=Yo, E=Et, sig=sig)

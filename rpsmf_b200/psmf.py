@@ -41,15 +41,19 @@ _HOOKS = ("inner", "_predictive_mean", "_predictive_covariance", "_predict_measu
 
 
 def _uniform_rho(R, d, what):
+    """diag(R): a float for R = rho * I, the (d,) vector for a non-uniform diagonal (psmf.py:144-152 takes the Woodbury
+    branch for any diagonal R); a non-diagonal R (the reference's O(d^3) fallback, psmf.py:150-152) is rejected."""
     R = np.asarray(R, dtype=np.float64)
     if R.ndim == 0:
         return float(R)
     if R.shape != (d, d):
         raise ValueError("%s must be (d, d)" % what)
     dg = np.diagonal(R)
-    if np.count_nonzero(R - np.diag(dg)) or not np.all(dg == dg[0]):
-        raise NotImplementedError("%s must be rho * I (diagonal, uniform); see rpsmf_b200/psmf.py" % what)
-    return float(dg[0])
+    if np.count_nonzero(R - np.diag(dg)):
+        raise NotImplementedError("%s must be diagonal; see rpsmf_b200/psmf.py" % what)
+    if np.all(dg == dg[0]):
+        return float(dg[0])
+    return np.ascontiguousarray(dg, dtype=np.float64)
 
 
 def _constant_over_k(D, what):
@@ -119,10 +123,11 @@ class PSMFIter:
 
     def _get_engine(self):
         if self._engine is None:
+            self._rho_vector = np.ndim(self._q_rho()[1]) != 0
             self._engine = FilterEngine(
                 self._d, self._r, dtype=self._dtype, robust=self._robust, simplified=self._simplified,
                 c_update_transpose=True, fixed_lambda=getattr(self, "fixed_lambda", False), ll_student=self._ll_student,
-                dynamics=self._dyn, alpha=self._alpha, beta=self._beta, device=self._device)
+                dynamics=self._dyn, alpha=self._alpha, beta=self._beta, device=self._device, rho_vector=self._rho_vector)
         return self._engine
 
     def _device_y(self, y, T, m=None):
@@ -174,7 +179,7 @@ class PSMFIter:
         if k0 == 0 or not getattr(self, "_state_on_device", False):
             Q, rho = self._q_rho()
             eng.set_state(C_=np.asarray(self._C[k0], dtype=np.float64), V=self._V[k0], P=self._P[k0],
-                          x=np.asarray(self._mu[k0], dtype=np.float64).reshape(-1), Q=Q, rho=[rho],
+                          x=np.asarray(self._mu[k0], dtype=np.float64).reshape(-1), Q=Q, rho=rho if np.ndim(rho) else [rho],
                           lam=[self._lambda_entering(k0)], theta=self._theta_vec(theta))
         else:
             eng.set_state(theta=self._theta_vec(theta))
@@ -247,7 +252,8 @@ class PSMFIter:
         if not getattr(self, "_state_on_device", False):
             Q, rho = self._q_rho()
             eng.set_state(C_=np.asarray(self._C[T], dtype=np.float64), V=self._V[T], P=self._P[T],
-                          x=np.asarray(self._mu[T], dtype=np.float64).reshape(-1), Q=Q, rho=[rho], lam=[self._lambda_entering(T)])
+                          x=np.asarray(self._mu[T], dtype=np.float64).reshape(-1), Q=Q, rho=rho if np.ndim(rho) else [rho],
+                          lam=[self._lambda_entering(T)])
         if self._dyn == _capi.DYN_EXTERNAL:
             # the callable lives on the host: roll mu out here (r values per step), project on the device
             mus, mu = [], self._mu[T]

@@ -75,10 +75,14 @@ class rPSMFIter(PSMFIter):
         return float(self.lambda0)
 
     def _after_sweep(self, st, k_last):
-        rho = float(st["rho"])
         self._Q = {k_last: st["Q"].cpu().numpy()}
-        # R = rho * I: materialised only for small d (the reference keeps a (d, d) array per step)
-        self._R = {k_last: rho * np.eye(self._d) if self._d <= 4096 else rho}
+        # R = rho * I (or diag(rho_i)): materialised only for small d (the reference keeps a (d, d) array per step)
+        if st["rho"].numel() > 1:
+            rv = st["rho"].cpu().numpy()
+            self._R = {k_last: np.diag(rv) if self._d <= 4096 else rv}
+        else:
+            rho = float(st["rho"])
+            self._R = {k_last: rho * np.eye(self._d) if self._d <= 4096 else rho}
         if not self.fixed_lambda:
             self._lambda = {k_last: float(st["lam"])}
 

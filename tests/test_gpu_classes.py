@@ -245,10 +245,40 @@ def test_hook_override_is_rejected():
         Bad(np.zeros((2, 1)), np.zeros((4, 2)), np.eye(2), np.zeros((2, 1)), np.eye(2), {0: np.eye(2)}, {0: np.eye(4)}, cosnl)
 
 
-def test_non_uniform_R_is_rejected():
+def test_non_diagonal_R_is_rejected():
     from rpsmf_b200 import PSMFIter
     R = np.diag([1.0, 2.0, 1.0, 1.0])
+    R[0, 1] = R[1, 0] = 0.1
     o = PSMFIter(np.zeros((2, 1)), np.zeros((4, 2)), np.eye(2), np.zeros((2, 1)), np.eye(2), {0: np.eye(2), 1: np.eye(2)},
                  {0: R, 1: R}, cosnl)
     with pytest.raises(NotImplementedError):
         o.step({1: np.zeros((4, 1))}, 1, 1)
+
+
+@pytest.mark.parametrize("tag,robust", [("diag_psmf", False), ("diag_rpsmf", True)])
+def test_diagonal_non_uniform_R_against_reference_fixture(tag, robust):
+    """R = diag(rho_i) with different rho_i (psmf.py:144-152 keeps the Woodbury branch for any diagonal R): the class
+    surface against the unmodified reference classes (tests/golden/make_golden.py make_diagR), incl. the theta gradient."""
+    from rpsmf_b200 import PSMFIter, rPSMFIter
+    g = load_golden("diag_R_cases")
+    Y = g[tag + "_Y"]
+    T, d = Y.shape
+    C0 = g[tag + "_C0"]
+    r = C0.shape[1]
+    R = np.diag(g[tag + "_rho_vec"])
+    th = g[tag + "_theta0"].reshape(r, 1)
+    if robust:
+        o = rPSMFIter(th, C0, g[tag + "_V0"], g[tag + "_mu0"].reshape(r, 1), g[tag + "_P0"], g[tag + "_Q"], R, float(g[tag + "_lam0"]), cosnl)
+    else:
+        o = PSMFIter(th, C0, g[tag + "_V0"], g[tag + "_mu0"].reshape(r, 1), g[tag + "_P0"], {k: g[tag + "_Q"] for k in range(T + 1)},
+                     {k: R for k in range(T + 1)}, cosnl)
+    o.step(_ydict(Y), 1, T)
+    yp = np.stack([o._y_pred[k].reshape(d) for k in range(1, T + 1)])
+    assert relerr(yp, g[tag + "_ypred"]) < TOL
+    assert relerr(o._C[T], g[tag + "_C"]) < TOL and relerr(o._mu[T].reshape(-1), g[tag + "_mu"]) < TOL
+    assert relerr(o._P[T], g[tag + "_P"]) < TOL and relerr(o._V[T], g[tag + "_V"]) < TOL
+    assert relerr(o._gradsum.reshape(-1), g[tag + "_gradsum"]) < GTOL       # the fixture's gradient is a finite difference
+    if robust:
+        assert relerr(np.diagonal(o._R[T]), g[tag + "_rho_vec_T"]) < TOL
+        assert abs(o._lambda[T] - float(g[tag + "_lam_T"])) < TOL * o._lambda[T]
+    o.close()

@@ -346,3 +346,31 @@ def test_full_size_batch_slice_properties():
     for s in pick:
         ost, oX, _, _ = _oracle_series(Y[s], M[s], C0[s], x0[s], init)
         assert relerr(Xa[s], oX) < TOL and relerr(Ca[s], ost.C) < TOL
+
+
+@pytest.mark.parametrize("method", ["rPSMF", "PSMF"])
+def test_impute_functions_with_non_uniform_diagonal_R(method):
+    """The two flat model functions with R = diag(rho_i), rho_i all different, against the UNMODIFIED reference functions
+    (fixture diag_R_cases.npz): Epred / Efull per sweep, the coverage, and the filtered X."""
+    from rpsmf_b200 import ProbabilisticSequentialMatrixFactorizer, robust_PSMF
+    g = load_golden("diag_R_cases")
+    Yorig = g["imp_Yorig"]
+    Mmiss = g["imp_Mmiss"].astype(np.float64)
+    Ymiss = Yorig.copy(); Ymiss[Mmiss == 1] = np.nan
+    M = (~np.isnan(Ymiss)).astype(np.int64)
+    Y = Ymiss.copy(); Y[np.isnan(Y)] = 0
+    YorigInt = Yorig.copy(); YorigInt[np.isnan(YorigInt)] = 0
+    d, n = Y.shape
+    r = g["imp_C0"].shape[1]
+    X = g["imp_X0"].copy()
+    pre = "imp_%s_" % method
+    R = np.diag(g["imp_rho_vec"])
+    V, Q, P = 2 * np.eye(r), 0.1 * np.eye(r), np.eye(r)
+    if method == "rPSMF":
+        ep, ef, rt, ib = robust_PSMF(Y, g["imp_C0"], X, d, n, r, M, Mmiss, V, Q, R, P, 1.8, 2, 2, YorigInt, float(g[pre + "Einit"]))
+    else:
+        ep, ef, rt, ib = ProbabilisticSequentialMatrixFactorizer(Y, g["imp_C0"], X, d, n, r, M, Mmiss, 0, V, Q, R, P, 2, 2, YorigInt,
+                                                                 float(g[pre + "Einit"]))
+    assert relerr(ep, g[pre + "Epred"]) < TOL and relerr(ef, g[pre + "Efull"]) < TOL
+    assert abs(ib - float(g[pre + "inside"])) < 1e-12
+    assert relerr(X, g[pre + "X_final"]) < TOL
