@@ -246,12 +246,8 @@ def bind_to_gpu_numa_node(torch, index):
     next are placed there (first touch): with several ranks per box, host buffers on a remote node halve the H2D rate.
     Returns a short description for the JSON line (None when the topology cannot be read)."""
     try:
-        bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
-        if bus is None:
-            out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
-                                 text=True, timeout=10).stdout.strip()
-            bus = out
-        bus = bus.lower()
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                             text=True, timeout=10).stdout.strip().lower()
         if len(bus.split(":")[0]) == 8:
             bus = bus[4:]                                          # 00000000:1B:00.0 -> 0000:1b:00.0
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())

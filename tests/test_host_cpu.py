@@ -86,8 +86,10 @@ def test_r_and_q_validation():
     from rpsmf_b200.psmf import _constant_over_k, _uniform_rho
     assert _uniform_rho(3.0 * np.eye(4), 4, "R") == 3.0
     assert _uniform_diag(10 * np.eye(5), 5, "R") == 10.0
+    assert np.array_equal(_uniform_rho(np.diag([1.0, 2.0]), 2, "R"), [1.0, 2.0])        # non-uniform diagonal: the vector
+    assert np.array_equal(_uniform_diag(np.diag([3.0, 2.0, 7.0]), 3, "R"), [3.0, 2.0, 7.0])
     with pytest.raises(NotImplementedError):
-        _uniform_rho(np.diag([1.0, 2.0]), 2, "R")
+        _uniform_rho(np.array([[1.0, 0.1], [0.1, 1.0]]), 2, "R")                       # not diagonal
     with pytest.raises(NotImplementedError):
         _uniform_diag(np.array([[1.0, 0.1], [0.1, 1.0]]), 2, "R")
     Q = np.eye(2)
