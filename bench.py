@@ -120,8 +120,9 @@ def regime_of(c_bytes):
     """Where the C shard of one GPU lives during a launch: decided by its size alone."""
     if c_bytes <= 147 * 112 * 1024:
         return "smem"            # resident in shared memory for the whole launch
-    if c_bytes <= 40e6:
-        return "l2"              # streams through the chunk ring but never leaves the 126 MB L2
+    if c_bytes <= 70e6:
+        return "l2"              # streams through the chunk ring but stays in the 126 MB L2 (ncu: 64 MB shard, 94.5 % L2 hits,
+                                 # DRAM 28 MB per step against 132 MB algorithmic: profiles/traffic_r02.json)
     if c_bytes <= 126e6:
         return "hbm+l2"          # streams from HBM, a large part of it still hits in L2
     return "hbm"
@@ -305,17 +306,22 @@ def measure_l2_copy_gbs(torch, dev, mbytes=16):
 
 
 def traffic_for(d_loc, r, dtype, W):
-    """DRAM bytes per launch from the committed ncu capture of the same shard size (profiles/traffic_r02.json), else None."""
-    for name in ("traffic_r02.json",):
-        p = os.path.join(ROOT, "profiles", name)
-        if os.path.exists(p):
-            try:
-                rec = json.load(open(p)).get("shards", {}).get("%d:%d:%s" % (d_loc, r, dtype))
-                if rec:
-                    return rec["dram_bytes_per_filter_step"] * W
-            except Exception:
-                pass
-    return None
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of the same
+    shard size (profiles/traffic_r02.json; the N-GPU shard profiled on one GPU -- the kernel's traffic depends on its rows
+    only), scaled by the row ratio when the shard differs by a tile or two; None when no capture within 1 % exists."""
+    p = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        best = None
+        for key, rec in json.load(open(p)).get("shards", {}).items():
+            rows, rr, dt = key.split(":")
+            if int(rr) == r and dt == dtype and abs(int(rows) - d_loc) <= 0.01 * d_loc:
+                if best is None or abs(int(rows) - d_loc) < abs(best[0] - d_loc):
+                    best = (int(rows), rec["dram_bytes_per_filter_step"])
+        return None if best is None else best[1] * (d_loc / best[0]) * W
+    except Exception:
+        return None
 
 
 # --------------------------------------------------------------------------------------------------

@@ -308,3 +308,32 @@ def predict(st: OracleState, cfg: OracleConfig, T, n_pred):
         mus.append(x.copy())
     mus = np.stack(mus)
     return mus, mus @ st.C.T
+
+
+def psmf_statespace_m(r, Y, Q, A, R, H, V, P0, C, X, m, n, X0):
+    """Line-by-line numpy restatement of ExperimentChange/PSMF.m:6-45 (linear dynamics A, observation selector H), with
+    the random initial state X0 of PSMF.m:12 passed in.  The Matlab reference cannot run here: this restatement is the
+    only checker of the (A, H) form -- PARITY UNPINNED against the Matlab code itself.  Returns (X, C, V, P)."""
+    C = np.array(C, dtype=np.float64); V = np.array(V, dtype=np.float64); X = np.array(X, dtype=np.float64)
+    P = np.array(P0, dtype=np.float64)
+    xprev = np.asarray(X0, dtype=np.float64).reshape(-1, 1)
+    for t in range(n):
+        Xp = A @ xprev                                                    # PSMF.m:13,29
+        PP = A @ P @ A.T + Q                                              # PSMF.m:14,30  (t = 1: A P0 A' + Q)
+        HX = H @ Xp
+        # PSMF.m:16,32 writes `barR = R + (H*Xp)'*V*(H*Xp)`: in Matlab a scalar added to a matrix lands on EVERY entry, which
+        # is not the model's Rbar = R + (x'Vx) I (psmf.py:141-143, rPSMF.py:92-98).  The model's form is restated here -- and
+        # implemented by rpsmf_b200.statespace; a literal port would add a rank-one all-ones term to S.
+        barR = R + float(HX.T @ V @ HX) * np.eye(m)
+        S = C @ (H @ PP @ H.T) @ C.T + barR                               # PSMF.m:17,33
+        e = Y[:, [t]] - C @ HX
+        Kg = PP @ H.T @ C.T @ np.linalg.inv(S)
+        xnew = Xp + Kg @ e                                                # PSMF.m:18,34
+        P = PP - Kg @ C @ H @ PP                                          # PSMF.m:19,35
+        eta = np.trace(C @ (H @ PP @ H.T) @ C.T + R) / m                  # PSMF.m:21,37
+        Nt = float(HX.T @ V @ HX) + eta                                   # PSMF.m:22,38
+        C = C + (e @ Xp.T @ H.T @ V) / Nt                                 # PSMF.m:24,40
+        V = V - (V @ H @ (Xp @ Xp.T) @ H.T @ V) / Nt                      # PSMF.m:25,41
+        X[:, [t]] = xnew
+        xprev = xnew
+    return X, C, V, P

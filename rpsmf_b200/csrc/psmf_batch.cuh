@@ -186,7 +186,14 @@ __global__ void __launch_bounds__(NW * 32, batch_min_ctas(R, NW)) psmf_batch_ker
         }
         __syncthreads();
         stamp(p, t, 5);
+#ifdef PSMF_BATCH_SOLO_UPDATE
+        // the r x r update on ONE warp (named barrier 1 / 2 over 32 threads): a quarter of the instruction issue of the
+        // CTA-wide version, the other warps' issue slots go to the series that share the SM
+        if (warp == 0) small_update<R, 32, 1, 2>(p, sh, tid, lane, warp, series, t, true, 32);
+        __syncthreads();
+#else
         small_update<R, NGJ>(p, sh, tid, lane, warp, series, t, true, NTHR);
+#endif
         stamp(p, t, 6);
     }
 

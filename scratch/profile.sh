@@ -1,14 +1,18 @@
 #!/bin/bash
-# ncu captures for profiles/: launch list of the bench command + full-set capture of the dominant kernel
-# (streaming regime d = 1M, and the shared-memory-resident regime of an 8-GPU shard, d = 125k)
-set -x
+# round-2 ncu captures for profiles/: launch list of the bench command, full-set captures of the pipelined kernel at the
+# shard sizes of 1 / 2 / 4 / 8 GPUs (per-launch DRAM traffic for roofline.traffic), and of the resident batch kernel
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01b_launches.csv \
-    python bench.py --steps 2 --warmup 1 --T 2000 --no-e2e --no-cpu > gpurun_out/r01b_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:psmf_ -s 2 -c 1 -f -o gpurun_out/r01b_stream_full \
-    python bench.py --T 400 --window 100 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/r01b_full.log 2>&1
-ncu -i gpurun_out/r01b_stream_full.ncu-rep --page raw --csv > gpurun_out/r01b_stream_full_raw.csv 2>/dev/null
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:psmf_ -s 2 -c 1 -f -o gpurun_out/r01b_resident_full \
-    python bench.py --d 125024 --T 800 --window 200 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/r01b_resident.log 2>&1
-ncu -i gpurun_out/r01b_resident_full.ncu-rep --page raw --csv > gpurun_out/r01b_resident_full_raw.csv 2>/dev/null
-ls -la gpurun_out/
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv \
+    python bench.py --steps 3 --warmup 3 --T 3000 --no-e2e --no-cpu > gpurun_out/r02_launches.log 2>&1; echo "launch list rc=$?"
+for rows in 1000000 500000 250000 124992; do
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:psmf_stream -s 2 -c 1 -f \
+      -o gpurun_out/r02_stream_full_$rows python bench.py --rows $rows --T 400 --window 100 --steps 2 --warmup 3 --no-e2e --no-cpu \
+      --parity-steps 0 > gpurun_out/r02_full_$rows.log 2>&1; echo "full $rows rc=$?"
+  ncu -i gpurun_out/r02_stream_full_$rows.ncu-rep --page raw --csv > gpurun_out/r02_stream_full_${rows}_raw.csv 2>/dev/null
+done
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:psmf_batch -s 2 -c 1 -f \
+    -o gpurun_out/r02_batch_full python bench.py --workload B --series 512 --T 500 --window 250 --steps 2 --warmup 3 --no-e2e --no-cpu \
+    --parity-steps 0 > gpurun_out/r02_batch_full.log 2>&1; echo "batch full rc=$?"
+ncu -i gpurun_out/r02_batch_full.ncu-rep --page raw --csv > gpurun_out/r02_batch_full_raw.csv 2>/dev/null
+rm -f gpurun_out/r02_stream_full_500000.ncu-rep gpurun_out/r02_stream_full_250000.ncu-rep     # keep the 64 MiB return budget
+ls -la gpurun_out/ | tail -20

@@ -374,3 +374,33 @@ def test_impute_functions_with_non_uniform_diagonal_R(method):
     assert relerr(ep, g[pre + "Epred"]) < TOL and relerr(ef, g[pre + "Efull"]) < TOL
     assert abs(ib - float(g[pre + "inside"])) < 1e-12
     assert relerr(X, g[pre + "X_final"]) < TOL
+
+
+def test_statespace_selector_form_against_restatement_of_PSMF_m():
+    """The (A, H) state-space form of ExperimentChange/PSMF.m through the rank-2r embedding C_eff = C H, V_eff = H'VH on the
+    CUDA engine, against a line-by-line numpy restatement of the Matlab function (oracle.psmf_statespace_m; the Matlab
+    reference cannot run here: parity unpinned beyond the restatement)."""
+    from rpsmf_b200 import statespace
+    rng = np.random.RandomState(12)
+    r, m, n = 4, 20, 150
+    s = 2 * r
+    a2 = np.array([[0.95, 0.05], [-0.1, 0.9]])
+    A = np.kron(np.eye(r), a2)                                   # main.m:68-70: kron(eye(r), .) blocks
+    Q = np.kron(np.eye(r), np.array([[0.02, 0.005], [0.005, 0.03]]))
+    H = np.kron(np.eye(r), np.array([[1.0, 0.0]]))               # selects the first component of every 2-dim block
+    V = np.eye(r)
+    P0 = np.eye(s)
+    C = rng.randn(m, r)
+    Ct = rng.randn(m, r)
+    x = rng.randn(s)
+    Y = np.zeros((m, n))
+    for t in range(n):
+        x = A @ x + 0.1 * rng.randn(s)
+        Y[:, t] = Ct @ (H @ x) + 0.05 * rng.randn(m)
+    X0 = np.linalg.cholesky(Q) @ rng.randn(s)
+    R = 0.001 * np.eye(m)
+    Xo, Co, Vo, Po = po.psmf_statespace_m(r, Y, Q, A, R, H, V, P0, C, np.zeros((s, n)), m, n, X0)
+    X = statespace.PSMF(r, Y, Q, A, R, H, V, P0, C, np.zeros((s, n)), m, n, x0=X0)
+    assert relerr(X, Xo) < TOL
+    assert relerr(statespace.PSMF.last["C"], Co) < TOL and relerr(statespace.PSMF.last["V"], Vo) < TOL
+    assert relerr(statespace.PSMF.last["P"], Po) < TOL

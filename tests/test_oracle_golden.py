@@ -229,3 +229,21 @@ def test_oracle_diagonal_nonuniform_R_impute(method):
     assert relerr(ep, g[pre + "Epred"]) < 1e-9 and relerr(ef, g[pre + "Efull"]) < 1e-9
     assert abs(ib - float(g[pre + "inside"])) < 1e-12
     assert relerr(X, g[pre + "X_final"]) < 1e-9
+
+
+def test_selector_form_of_PSMF_m_is_the_rank_2r_standard_step():
+    """ExperimentChange/PSMF.m (linear dynamics A, observation selector H) restated line by line equals the standard PSMF
+    step of rank 2r on C_eff = C H, V_eff = H'VH with linear dynamics: the identity rpsmf_b200.statespace relies on."""
+    rng = np.random.RandomState(12)
+    r, m, n = 4, 20, 60
+    s = 2 * r
+    A = np.kron(np.eye(r), np.array([[0.95, 0.05], [-0.1, 0.9]]))
+    Q = np.kron(np.eye(r), np.array([[0.02, 0.005], [0.005, 0.03]]))
+    H = np.kron(np.eye(r), np.array([[1.0, 0.0]]))
+    V, P0, C = np.eye(r), np.eye(s), rng.randn(m, r)
+    Y, X0, R = rng.randn(m, n), rng.randn(s), 0.001 * np.eye(m)
+    Xo, Co, Vo, Po = po.psmf_statespace_m(r, Y, Q, A, R, H, V, P0, C, np.zeros((s, n)), m, n, X0)
+    cfg = po.OracleConfig(robust=False, c_update_transpose=False, dynamics=po.DYN_LINEAR, lin_A=A)
+    st = po.OracleState(C @ H, X0.copy(), P0.copy(), H.T @ V @ H, Q.copy(), 0.001, 0.0)
+    st, X, _, _ = po.run(st, cfg, Y.T.copy(), None)
+    assert relerr(X.T, Xo) < 1e-12 and relerr(st.C @ H.T, Co) < 1e-12 and relerr(H @ st.V @ H.T, Vo) < 1e-12 and relerr(st.P, Po) < 1e-12
