@@ -324,14 +324,14 @@ def psmf_statespace_m(r, Y, Q, A, R, H, V, P0, C, X, m, n, X0):
         # PSMF.m:16,32 writes `barR = R + (H*Xp)'*V*(H*Xp)`: in Matlab a scalar added to a matrix lands on EVERY entry, which
         # is not the model's Rbar = R + (x'Vx) I (psmf.py:141-143, rPSMF.py:92-98).  The model's form is restated here -- and
         # implemented by rpsmf_b200.statespace; a literal port would add a rank-one all-ones term to S.
-        barR = R + float(HX.T @ V @ HX) * np.eye(m)
+        barR = R + (HX.T @ V @ HX).item() * np.eye(m)
         S = C @ (H @ PP @ H.T) @ C.T + barR                               # PSMF.m:17,33
         e = Y[:, [t]] - C @ HX
         Kg = PP @ H.T @ C.T @ np.linalg.inv(S)
         xnew = Xp + Kg @ e                                                # PSMF.m:18,34
         P = PP - Kg @ C @ H @ PP                                          # PSMF.m:19,35
         eta = np.trace(C @ (H @ PP @ H.T) @ C.T + R) / m                  # PSMF.m:21,37
-        Nt = float(HX.T @ V @ HX) + eta                                   # PSMF.m:22,38
+        Nt = (HX.T @ V @ HX).item() + eta                                   # PSMF.m:22,38
         C = C + (e @ Xp.T @ H.T @ V) / Nt                                 # PSMF.m:24,40
         V = V - (V @ H @ (Xp @ Xp.T) @ H.T @ V) / Nt                      # PSMF.m:25,41
         X[:, [t]] = xnew
