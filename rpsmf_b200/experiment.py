@@ -85,14 +85,18 @@ def _default_fit(method):
     return robust_PSMF if method == "rPSMF" else ProbabilisticSequentialMatrixFactorizer
 
 
-def run_impute_experiment(Yorig, method="rPSMF", percentage=30, seed=None, repeats=1, fit=None, log=None, **hyper):
+def run_impute_experiment(Yorig, method="rPSMF", percentage=30, seed=None, repeats=1, fit=None, log=None, batched=False, **hyper):
     """Repeat the imputation fit ``repeats`` times on fresh random masks / initialisations.
 
     ``Yorig`` (d, T) float64 with NaN at originally missing entries.  ``fit`` defaults to the CUDA model function of
     ``method`` (``robust_PSMF`` / ``ProbabilisticSequentialMatrixFactorizer``); any callable with the same positional
     signature works (the CPU tests pass the oracle).  Returns the result record of ``prepare_output``
     (common.py:114-146) without the host / script provenance fields: ``method, seed, missing_percentage,
-    missing_ratio, parameters, hashes{Y,C,X}, results{error_predict, error_full, runtime, inside_sig}``."""
+    missing_ratio, parameters, hashes{Y,C,X}, results{error_predict, error_full, runtime, inside_sig}``.
+
+    ``batched=True`` draws the inputs of all repeats first (the fits consume no random numbers, so the stream -- and the
+    ``hashes`` -- are unchanged) and filters the repeats side by side on the resident batch kernel
+    (``rpsmf_b200.impute.fit_repeats``): the 100-repeat loop of the reference as one launch per sweep."""
     if method not in ("rPSMF", "PSMF"):
         raise ValueError("method must be 'rPSMF' or 'PSMF'")
     hp = dict(DEFAULTS)
@@ -116,6 +120,32 @@ def run_impute_experiment(Yorig, method="rPSMF", percentage=30, seed=None, repea
     res = dict(error_predict=[], error_full=[], runtime=[], inside_sig=[])
     hashes = dict(Y=[], C=[], X=[])
     missRatio = float("nan")
+    if batched:
+        if fit is not None:
+            raise ValueError("batched=True uses the CUDA batch kernel; it takes no custom fit")
+        from .impute import fit_repeats
+        Ys, Cs, Xs, Ms, Mms, Eis = [], [], [], [], [], []
+        for i in range(repeats):
+            Ymiss = np.copy(Yorig)
+            missRatio, missMask = prepare_missing(Ymiss, percentage / 100)
+            M = np.array(np.invert(np.isnan(Ymiss)), dtype=int)
+            Y = np.copy(Ymiss)
+            Y[np.isnan(Y)] = 0
+            C = np.random.rand(d, r)
+            X = np.random.rand(r, T)
+            hashes["Y"].append(matrix_hash(Y)); hashes["C"].append(matrix_hash(C)); hashes["X"].append(matrix_hash(X))
+            Ys.append(Y); Cs.append(C); Xs.append(X); Ms.append(M); Mms.append(missMask)
+            Eis.append(rmsem(C @ X, YorigInt, missMask))
+        eps, efs, rts, ibs = fit_repeats(Ys, Cs, Xs, Ms, Mms, V, Q, R, P, hp["lambda0"], hp["sig"], Iter, YorigInt, Eis,
+                                         robust=method == "rPSMF")
+        for ep, ef, rt, ib in zip(eps, efs, rts, ibs):
+            e_pred, e_full = float(ep[:, Iter].item()), float(ef[:, Iter].item())
+            bad = np.isnan(e_pred) or np.isnan(e_full)
+            res["error_predict"].append(e_pred)
+            res["error_full"].append(e_full)
+            res["runtime"].append(float("nan") if bad else float(rt[:, Iter].item()))
+            res["inside_sig"].append(float("nan") if bad else float(ib))
+        repeats = 0
     for i in range(repeats):
         Ymiss = np.copy(Yorig)
         missRatio, missMask = prepare_missing(Ymiss, percentage / 100)

@@ -106,3 +106,60 @@ def robust_PSMF(Y, C, X, d, n, r, M, Mmiss, V, Q0, R0, P, lambda0, sig, Iter, Yo
 def ProbabilisticSequentialMatrixFactorizer(Y, C, X, d, n, r, M, Mmiss, lam, V, Q, R, P, sig, Iter, YorgInt, Einit):
     """ExperimentImpute/PSMF.py:40-42 signature (``lam`` is unused there too)."""
     return _fit(Y, C, X, d, n, r, M, Mmiss, V, Q, R, P, 0.0, sig, Iter, YorgInt, Einit, robust=False)
+
+
+def fit_repeats(Ys, Cs, Xs, Ms, Mmisses, V, Q0, R0, P, lambda0, sig, Iter, YorigInt, Einits, robust=True, device=None,
+                dtype=torch.float64):
+    """All repeats of the imputation experiment in ONE batch (the 100-repeat loop of ExperimentImpute/rPSMF.py:194-232 /
+    PSMF.py:140-178): repeat k has its own random mask and initial C, X but the same data set, so the repeats are
+    independent series of equal shape -- the resident batch kernel filters them side by side, one CTA each, C in shared
+    memory.  Arguments are lists over the repeats of what ``robust_PSMF`` / ``ProbabilisticSequentialMatrixFactorizer``
+    take per call; returns the lists ``(Epred, Efull, RunTime, InsideBars)`` of what they return per call.  ``Xs[k]`` is
+    overwritten in place like ``X`` there."""
+    S = len(Ys)
+    d, n = np.asarray(Ys[0]).shape
+    r = np.asarray(Cs[0]).shape[1]
+    rho0 = _uniform_diag(R0, d, "R")
+    if np.ndim(rho0) != 0:
+        raise NotImplementedError("fit_repeats runs on the batch kernel: R must be rho * I (use the per-repeat functions)")
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    t0 = time.time()
+    Yt = torch.stack([ingest(Ys[k], dtype=dtype, keep_nan=False, want_mask=False, device=dev.index)[0] for k in range(S)])
+    Mt = torch.stack([transpose_mask(Ms[k], device=dev.index) for k in range(S)])
+    Et = torch.stack([transpose_mask(Mmisses[k], device=dev.index) for k in range(S)])
+    Yo1, _ = ingest(YorigInt, dtype=dtype, keep_nan=False, want_mask=False, device=dev.index)
+    Yo = Yo1.unsqueeze(0).expand(S, n, d).contiguous()
+    eng = FilterEngine(d, r, n_series=S, dtype=dtype, robust=robust, c_update_transpose=robust, dynamics=_capi.DYN_IDENTITY,
+                       device=dev.index)
+    Epred = [np.zeros([1, Iter + 1]) for _ in range(S)]
+    Efull = [np.zeros([1, Iter + 1]) for _ in range(S)]
+    RunTime = [np.zeros([1, Iter + 1]) for _ in range(S)]
+    Inside = [0.0] * S
+    for k in range(S):
+        Epred[k][:, 0] = Einits[k]; Efull[k][:, 0] = Einits[k]
+    try:
+        eng.set_state(C_=np.stack([np.asarray(c, dtype=np.float64) for c in Cs]), V=V, P=P,
+                      x=np.stack([np.ascontiguousarray(np.asarray(x)[:, n - 1]) for x in Xs]), Q=Q0, rho=[rho0],
+                      lam=[lambda0 if robust else 0.0])
+        for i in range(Iter):
+            if robust:
+                eng.set_state(Q=Q0, rho=[rho0], lam=[lambda0])                 # rPSMF.py:77-79
+            out = eng.run(Yt, Mt, k0=1, want_X=True, Yorig=Yo, E=Et, sig=sig)
+            bad = eng.status()
+            ev = out["eval"].cpu().numpy().reshape(S, -1)
+            Xd = out["X"].reshape(S, n, r)
+            ef = eng.eval_full(Xd, Yo, Et).cpu().numpy().reshape(S, 2)
+            Xh = Xd.cpu().numpy()
+            for k in range(S):
+                Xs[k][:, :] = Xh[k].T
+                Epred[k][:, i + 1] = np.sqrt(ev[k, _capi.EVAL_SSE] / ev[k, _capi.EVAL_COUNT])
+                Efull[k][:, i + 1] = np.sqrt(ef[k, 0] / ef[k, 1])
+                Inside[k] = float(ev[k, _capi.EVAL_INSIDE] / ev[k, _capi.EVAL_COUNT])
+                if bad >= 0 and not np.isfinite(Xh[k]).all():
+                    Epred[k][:, i + 1] = np.nan; Efull[k][:, i + 1] = np.nan
+                RunTime[k][:, i + 1] = (time.time() - t0) / S                  # wall time of the batch, shared evenly
+        info = eng.launch_info()
+    finally:
+        eng.close()
+    fit_repeats.last_launch = info
+    return Epred, Efull, RunTime, Inside

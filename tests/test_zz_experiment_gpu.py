@@ -50,3 +50,23 @@ def test_c_demo_runs_on_the_gpu():
             assert "kernel=" + kernel in r.stdout and "first_bad_step=-1" in r.stdout, r.stdout
             xs = [float(v) for v in r.stdout.strip().splitlines()[-1].split()[2:]]
             assert len(xs) == int(args[1]) and all(np.isfinite(xs))
+
+
+@pytest.mark.parametrize("method", ["rPSMF", "PSMF"])
+def test_batched_repeats_equal_the_repeat_loop(method):
+    """The 100-repeat loop of the imputation experiment (rPSMF.py:194-232) as ONE batch on the resident batch kernel:
+    same random stream (hashes), and per repeat the same errors / coverage as the loop over the per-repeat functions."""
+    rng = np.random.RandomState(3)
+    d, T, r = 27, 220, 6
+    Ct = rng.randn(d, r)
+    x = np.cumsum(0.1 * rng.randn(T, r), axis=0)
+    Yorig = (x @ Ct.T).T + 0.3 * rng.standard_t(3, (d, T))
+    Yorig[rng.rand(d, T) < 0.03] = np.nan
+    a = ex.run_impute_experiment(Yorig, method, 30, seed=77, repeats=6, r=r)
+    b = ex.run_impute_experiment(Yorig, method, 30, seed=77, repeats=6, r=r, batched=True)
+    assert a["hashes"] == b["hashes"] and a["missing_ratio"] == b["missing_ratio"]
+    from rpsmf_b200.impute import fit_repeats
+    assert fit_repeats.last_launch["kernel"] == "batch"
+    for key in ("error_predict", "error_full"):
+        assert np.allclose(a["results"][key], b["results"][key], rtol=1e-9, atol=0)
+    assert a["results"]["inside_sig"] == b["results"]["inside_sig"]
