@@ -33,7 +33,8 @@ struct YMreg {
 template <int R, typename T, int NW>
 __global__ void __launch_bounds__(NW * 32, batch_min_ctas(R, NW)) psmf_batch_kernel(const KParams p) {
     constexpr int NSP = nstat_pad(R), NST = nstat(R), NTHR = NW * 32;
-    constexpr int NGJ = NTHR < GJ_THREADS ? NTHR : GJ_THREADS;
+    // elimination threads: all but one warp, which computes the inverse-free half of the r x r update meanwhile
+    constexpr int NGJ = (NTHR - 32) < GJ_THREADS ? (NTHR - 32) : GJ_THREADS;
     extern __shared__ __align__(128) unsigned char dyn_smem_b[];
     __shared__ Smem<R> sh;
     __shared__ double red[NW * nstat_pad(R)];
@@ -126,19 +127,19 @@ __global__ void __launch_bounds__(NW * 32, batch_min_ctas(R, NW)) psmf_batch_ker
                 }
             }
         }
-#pragma unroll 1
-        for (int q = 0; warp + q * NW < ntiles; ++q) {
+        // ---- the pass: one warp per resident tile, lane = row.  r <= 8: TWO tiles per iteration, written load / compute /
+        // store stage by stage so that the two independent instruction streams interleave (the tile is latency-bound: at
+        // 14 warps per SM a single stream leaves the shared-memory and fp64 pipes two thirds idle); their Gram DMMAs go to
+        // two accumulators.  Tiles of a warp: warp, warp + NW, ...
+        auto load_tile = [&](int q, double (&c)[R], double& ep, double& yi, bool& mi, bool& inb, int& rl, int64_t& row) -> T* {
             const int tile = warp + q * NW;
-            const int64_t row = (int64_t)tile * TILE + lane;
-            const int rl = tile * TILE + lane;
-            const bool inb = row < p.d;
+            row = (int64_t)tile * TILE + lane;
+            rl = tile * TILE + lane;
+            inb = row < p.d;
             T* tl = Ct + (size_t)tile * (R * TILE);
-            double c[R];
 #pragma unroll
             for (int j = 0; j < R; ++j) c[j] = (double)tl[tile_pos(j, lane)];
-            const double ep = ebuf[rl];
-            double yi;
-            bool mi;
+            ep = ebuf[rl];
             if (q < V3_PF) {
                 // select the prefetched pair without dynamic register indexing
                 T yr = cur[0].y;
@@ -153,18 +154,54 @@ __global__ void __launch_bounds__(NW * 32, batch_min_ctas(R, NW)) psmf_batch_ker
             } else {
                 observe<T>(p, Yt, Mt, row, inb, yi, mi);
             }
-            if (evalon && t > 0) eval_cover(ev, eb, rl, sh.sc[7], sh.sc[1], sh.sc[2], robust, p.sig);
-            double e, yh;
-            row_stats<R>(acc, sh, c, ep, inb, mi, yi, w1, w0, e, yh);
+            return tl;
+        };
+        auto store_tile = [&](T* tl, const double (&c)[R], double e, double yh, bool mi, bool inb, int rl, int64_t row) {
 #pragma unroll
             for (int j = 0; j < R; ++j) tl[tile_pos(j, lane)] = (T)c[j];
             ebuf[rl] = e;
             if (Yrec_t != nullptr && inb) Yrec_t[row] = (T)yh;
             if (evalon) eval_row(ev, eb, rl, inb && Et[row] != 0, mi, yh, inb ? (double)Yo_t[row] : 0.0);
-            const unsigned mbits = __ballot_sync(FULL, mi);
-            __syncwarp();
-            tile_gram<R, T>(acc, tl, mbits, lane);               // straight from the resident tile
-            __syncwarp();
+        };
+        constexpr bool PAIR = R <= 8;
+#pragma unroll 1
+        for (int q = 0; warp + q * NW < ntiles; q += PAIR ? 2 : 1) {
+            bool paired = false;
+            if constexpr (PAIR) paired = warp + (q + 1) * NW < ntiles;
+            if constexpr (PAIR) if (paired) {
+                double cA[R], cB[R], epA, epB, yiA, yiB, eA, eB, yhA, yhB;
+                bool miA, miB, inbA, inbB;
+                int rlA, rlB;
+                int64_t rowA, rowB;
+                T* tlA = load_tile(q, cA, epA, yiA, miA, inbA, rlA, rowA);
+                T* tlB = load_tile(q + 1, cB, epB, yiB, miB, inbB, rlB, rowB);
+                if (evalon && t > 0) {
+                    eval_cover(ev, eb, rlA, sh.sc[7], sh.sc[1], sh.sc[2], robust, p.sig);
+                    eval_cover(ev, eb, rlB, sh.sc[7], sh.sc[1], sh.sc[2], robust, p.sig);
+                }
+                row_stats<R>(acc, sh, cA, epA, inbA, miA, yiA, w1, w0, eA, yhA);
+                row_stats<R>(acc, sh, cB, epB, inbB, miB, yiB, w1, w0, eB, yhB);
+                store_tile(tlA, cA, eA, yhA, miA, inbA, rlA, rowA);
+                store_tile(tlB, cB, eB, yhB, miB, inbB, rlB, rowB);
+                const unsigned mbA = __ballot_sync(FULL, miA), mbB = __ballot_sync(FULL, miB);
+                __syncwarp();
+                tile_gram2<R, T>(acc, tlA, mbA, tlB, mbB, lane);     // straight from the resident tiles
+                __syncwarp();
+            }
+            if (!paired) {
+                double c[R], ep, yi, e, yh;
+                bool mi, inb;
+                int rl;
+                int64_t row;
+                T* tl = load_tile(q, c, ep, yi, mi, inb, rl, row);
+                if (evalon && t > 0) eval_cover(ev, eb, rl, sh.sc[7], sh.sc[1], sh.sc[2], robust, p.sig);
+                row_stats<R>(acc, sh, c, ep, inb, mi, yi, w1, w0, e, yh);
+                store_tile(tl, c, e, yh, mi, inb, rl, row);
+                const unsigned mbits = __ballot_sync(FULL, mi);
+                __syncwarp();
+                tile_gram<R, T>(acc, tl, mbits, lane);               // straight from the resident tile
+                __syncwarp();
+            }
         }
         stamp(p, t, 1);
         acc_writeout<R>(acc, red + warp * NSP, w1, lane);
@@ -186,14 +223,7 @@ __global__ void __launch_bounds__(NW * 32, batch_min_ctas(R, NW)) psmf_batch_ker
         }
         __syncthreads();
         stamp(p, t, 5);
-#ifdef PSMF_BATCH_SOLO_UPDATE
-        // the r x r update on ONE warp (named barrier 1 / 2 over 32 threads): a quarter of the instruction issue of the
-        // CTA-wide version, the other warps' issue slots go to the series that share the SM
-        if (warp == 0) small_update<R, 32, 1, 2>(p, sh, tid, lane, warp, series, t, true, 32);
-        __syncthreads();
-#else
         small_update<R, NGJ>(p, sh, tid, lane, warp, series, t, true, NTHR);
-#endif
         stamp(p, t, 6);
     }
 

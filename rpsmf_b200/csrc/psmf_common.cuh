@@ -40,7 +40,10 @@ __host__ __device__ constexpr int tile_pos(int j, int i) { return j * 32 + (i ^ 
 constexpr int V1_WARPS = 8;     // direct-load kernel: warps per CTA (one tile per warp at a time)
 constexpr int V3_PF = 4;        // resident batch kernel: tiles per warp whose y / m are prefetched one step ahead
 // resident batch kernel: CTAs per SM the register budget is sized for (shared memory permitting)
-__host__ __device__ constexpr int batch_min_ctas(int R, int NW) { return NW >= 8 ? 2 : (R <= 8 ? 5 : (R <= 12 ? 4 : 3)); }
+#ifndef PSMF_BATCH_MIN_R8
+#define PSMF_BATCH_MIN_R8 4
+#endif
+__host__ __device__ constexpr int batch_min_ctas(int R, int NW) { return NW >= 8 ? 2 : (R <= 8 ? PSMF_BATCH_MIN_R8 : (R <= 12 ? 4 : 3)); }
 constexpr int V2_CWARPS = 14;   // TMA-staged kernel: pass warps (+1 reduce warp, +1 producer warp)
 // TMA-staged kernel: tiles per shared-memory chunk slot.  The single-thread bulk-copy loop costs ~0.6 us per iteration
 // whatever the chunk size (scratch/bulkbench.cu), so a chunk must carry ~16 KB to sustain the HBM rate: 4 tiles at

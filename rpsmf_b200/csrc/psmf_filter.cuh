@@ -240,9 +240,10 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
 template <int R>
 struct TileAcc {
     double g00[2], g01[2], g11[2];   // fragments of sum_i m_i c_i c_i' : blocks (0..7,0..7), (0..7,8..15), (8..15,8..15)
+    double g00x[2];                  // r <= 8: second accumulator of block (0,0) -- two independent DMMA chains instead of one
     double v[R + 4];                 // per-lane: b (R), s, q1, q0, n_obs
     __device__ __forceinline__ void zero() {
-        g00[0] = g00[1] = g01[0] = g01[1] = g11[0] = g11[1] = 0.0;
+        g00[0] = g00[1] = g01[0] = g01[1] = g11[0] = g11[1] = g00x[0] = g00x[1] = 0.0;
 #pragma unroll
         for (int i = 0; i < R + 4; ++i) v[i] = 0.0;
     }
@@ -281,13 +282,34 @@ __device__ __forceinline__ void tile_gram(TileAcc<R>& A, const TS* __restrict__ 
         const int pos = row ^ (mm << 2);                       // tile_pos(mm, row) - mm*32 == tile_pos(8+mm, row) - (8+mm)*32
         const double a0 = (mm < R) ? (double)tile[mm * 32 + pos] : 0.0;
         const double b0 = mrow ? a0 : 0.0;
-        dmma884(A.g00, a0, b0);
         if constexpr (R > 8) {
+            dmma884(A.g00, a0, b0);
             const double a1 = (8 + mm < R) ? (double)tile[(8 + mm) * 32 + pos] : 0.0;
             const double b1 = mrow ? a1 : 0.0;
             dmma884(A.g01, a0, b1);
             dmma884(A.g11, a1, b1);
+        } else {
+            // a single block: alternate between two accumulators so that consecutive DMMAs do not wait for each other
+            if (s & 1) dmma884(A.g00x, a0, b0);
+            else dmma884(A.g00, a0, b0);
         }
+    }
+}
+
+// two tiles at once (r <= 8): tile A accumulates into g00, tile B into g00x -- two independent DMMA chains
+template <int R, typename TS>
+__device__ __forceinline__ void tile_gram2(TileAcc<R>& A, const TS* __restrict__ ta, unsigned mba, const TS* __restrict__ tb, unsigned mbb,
+                                           int lane) {
+    static_assert(R <= 8, "tile_gram2 is the single-block form");
+    const int kk = lane & 3, mm = lane >> 2;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const int row = 4 * s + kk;
+        const int pos = row ^ (mm << 2);
+        const double a = (mm < R) ? (double)ta[mm * 32 + pos] : 0.0;
+        const double b = (mm < R) ? (double)tb[mm * 32 + pos] : 0.0;
+        dmma884(A.g00, a, ((mba >> row) & 1u) ? a : 0.0);
+        dmma884(A.g00x, b, ((mbb >> row) & 1u) ? b : 0.0);
     }
 }
 
@@ -298,7 +320,7 @@ __device__ __forceinline__ void acc_writeout(TileAcc<R>& A, double* __restrict__
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
         const int n = 2 * kk + x;
-        if (mm <= n && n < R) red[gram_off(R, mm) + (n - mm)] = w1 * A.g00[x];
+        if (mm <= n && n < R) red[gram_off(R, mm) + (n - mm)] = w1 * (R > 8 ? A.g00[x] : A.g00[x] + A.g00x[x]);
         if constexpr (R > 8) {
             if (8 + n < R) red[gram_off(R, mm) + (8 + n - mm)] = w1 * A.g01[x];
             if (mm <= n && 8 + n < R) red[gram_off(R, 8 + mm) + (n - mm)] = w1 * A.g11[x];
@@ -580,6 +602,10 @@ __device__ void gauss_jordan_cta(Smem<R>& sh, int tid) {
 }
 
 // ---- r x r part of the step (rPSMF.py:102-115,133-135), identical on every CTA; all `nthr` threads ----
+// Two halves.  eta, N, phi, the update of V and the rank-1 direction g need the reduced statistics but NOT the inverse:
+// when the CTA has a warp outside the NGJ elimination threads (nthr >= NGJ + 32) that warp computes them WHILE the
+// Gauss-Jordan elimination runs; x, omega, P, Q, rho, lambda follow the elimination.  The arithmetic is the same either
+// way (bit-identical results), only the schedule differs.
 template <int R, int NGJ, int BAR = 0, int GJBAR = 1>
 __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, int warp, int series, int64_t t,
                              bool writer, int nthr, const double* totv = nullptr) {
@@ -592,6 +618,46 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
     const bool rhov = totv != nullptr;
     const double* tot = rhov ? totv : sh.tot;
     const double* G0p = rhov ? totv + sv_G0(R) : sh.tot;
+    const double dg = (double)p.d_global;
+    const bool side_warp = !simp && nthr >= NGJ + 32;          // a whole warp next to the elimination threads
+
+    // the half that does not need the inverse, executed by ONE warp (all 32 lanes): eta, N, phi -> sc[1..3,5,7], V, g
+    auto side_half = [&]() {
+        const double a = sh.a, rho = sh.rho, lam = sh.lam;
+        const double q1 = tot[NGm + R + 1], q0 = tot[NGm + R + 2], nobs = tot[NGm + R + 3];
+        double trpg = 0.0;
+        if (!simp && lane < R) {
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < R; i += 2) {
+                const int lo = i < lane ? i : lane, hi = i < lane ? lane : i;
+                t0 = fma(sh.Pb[i * R + lane], G0p[gram_off(R, lo) + hi - lo], t0);
+                if (i + 1 < R) {
+                    const int lo1 = i + 1 < lane ? i + 1 : lane, hi1 = i + 1 < lane ? lane : i + 1;
+                    t1 = fma(sh.Pb[(i + 1) * R + lane], G0p[gram_off(R, lo1) + hi1 - lo1], t1);
+                }
+            }
+            trpg = t0 + t1;
+        }
+        trpg = warp_allsum(trpg);
+        double eta;
+        if (simp) eta = rhov ? rho * p.rho_mean[series] : rho;                 // tr(R)/d, synthetic_psmf.py:86-87
+        // rPSMF.py:108: trace(M R M + CM Pbar CM') / d; uniform R: sum m c c' = (rho + a) G
+        else eta = rhov ? (tot[sv_nrho(R)] + trpg) / dg : (rho * nobs + (rho + a) * trpg) / dg;
+        const double N = a + eta;                                              // rPSMF.py:109
+        const double phi = robust ? (lam + q1 / (a + eta) + (q0 != 0.0 ? q0 / eta : 0.0)) / (lam + dg) : 1.0;
+        const double aphi = p.alpha * phi;
+        for (int idx = lane; idx < R * R; idx += 32) {
+            const int i = idx / R, j = idx % R;
+            sh.V[idx] = aphi * (sh.V[idx] - sh.vx[i] * sh.vxt[j] / N);         // rPSMF.py:115
+        }
+        if (lane < R) sh.g[lane] = (((p.flags & F_CUPDATE_VT) != 0) ? sh.vx[lane] : sh.vxt[lane]) / N;   // rPSMF.py:111 / PSMF.py:80
+        if (lane == 0) {
+            sh.sc[1] = eta; sh.sc[2] = N; sh.sc[3] = phi; sh.sc[5] = aphi;
+            sh.sc[7] = a;                                  // a of THIS step (sh.a is overwritten by the next predict)
+        }
+    };
+
     if (!simp) {
         for (int idx = tid; idx < R * R; idx += nthr) {
             const int i = idx / R, j = idx % R;
@@ -613,16 +679,21 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         }
         sync_n<BAR>(nthr);
         // the elimination is latency-bound: a subset of the warps runs it (less redundant pivot-search work on
-        // the fp64 pipe, cheaper barrier), the others wait at the CTA barrier below
+        // the fp64 pipe, cheaper barrier); the first warp past them computes the inverse-free half meanwhile
         if (tid < NGJ) gauss_jordan_cta<R, NGJ, GJBAR>(sh, tid);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
+        else if (side_warp && warp == NGJ / 32) side_half();
         sync_n<BAR>(nthr);
     }
     stamp(p, t, 7);
     if (warp == 0) {
+        if (!side_warp) {
+            side_half();
+            __syncwarp();
+        }
         const double a = sh.a, rho = sh.rho, lam = sh.lam;
-        const double s = tot[NGm + R], q1 = tot[NGm + R + 1], q0 = tot[NGm + R + 2], nobs = tot[NGm + R + 3];
-        const double dg = (double)p.d_global;
-        double xn = 0.0, bkb = 0.0, trpg = 0.0;
+        const double s = tot[NGm + R], q1 = tot[NGm + R + 1], nobs = tot[NGm + R + 3];
+        const double eta = sh.sc[1], N = sh.sc[2], phi = sh.sc[3];
+        double xn = 0.0, bkb = 0.0;
         if (lane < R) {
             if (simp) {
                 xn = sh.xb[lane];                                              // synthetic_psmf.py:93-94
@@ -630,33 +701,11 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
                 const double kb = sh.aug[FIN][sh.perm[lane]][2 * R];
                 xn = sh.xb[lane] + kb;                                         // rPSMF.py:104
                 bkb = tot[NGm + lane] * kb;
-                double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-                for (int i = 0; i < R; i += 2) {
-                    const int lo = i < lane ? i : lane, hi = i < lane ? lane : i;
-                    t0 = fma(sh.Pb[i * R + lane], G0p[gram_off(R, lo) + hi - lo], t0);
-                    if (i + 1 < R) {
-                        const int lo1 = i + 1 < lane ? i + 1 : lane, hi1 = i + 1 < lane ? lane : i + 1;
-                        t1 = fma(sh.Pb[(i + 1) * R + lane], G0p[gram_off(R, lo1) + hi1 - lo1], t1);
-                    }
-                }
-                trpg = t0 + t1;
             }
         }
         bkb = warp_allsum(bkb);
-        trpg = warp_allsum(trpg);
-        double sSe, eta;
-        if (simp) {
-            sSe = s;                                                           // synthetic_rpsmf.py:93-98
-            eta = rhov ? rho * p.rho_mean[series] : rho;                       // tr(R)/d, synthetic_psmf.py:86-87
-        } else {
-            sSe = s - bkb;                                                     // diff' CPinv diff
-            // rPSMF.py:108: trace(M R M + CM Pbar CM') / d; uniform R: sum m c c' = (rho + a) G
-            eta = rhov ? (tot[sv_nrho(R)] + trpg) / dg : (rho * nobs + (rho + a) * trpg) / dg;
-        }
+        const double sSe = simp ? s : s - bkb;                                 // diff' CPinv diff (synthetic_rpsmf.py:93-98: s)
         const double omega = robust ? (lam + sSe) / (lam + dg) : 1.0;          // rPSMF.py:105
-        const double N = a + eta;                                              // rPSMF.py:109
-        const double phi = robust ? (lam + q1 / (a + eta) + (q0 != 0.0 ? q0 / eta : 0.0)) / (lam + dg) : 1.0;
         if (lane < R) {
             sh.x[lane] = xn;
             if (writer && p.X_out != nullptr) p.X_out[((int64_t)series * p.n_steps + t) * R + lane] = xn;
@@ -679,9 +728,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
             }
         }
         if (lane == 0) {
-            sh.sc[0] = omega; sh.sc[1] = eta; sh.sc[2] = N; sh.sc[3] = phi; sh.sc[4] = sSe;
-            sh.sc[5] = p.alpha * phi; sh.sc[6] = p.beta * omega;
-            sh.sc[7] = a;                                  // a of THIS step (sh.a is overwritten by the next predict)
+            sh.sc[0] = omega; sh.sc[4] = sSe; sh.sc[6] = p.beta * omega;
             if (writer) {
                 if (p.scal_out != nullptr) {
                     double* so = p.scal_out + ((int64_t)series * p.n_steps + t) * NSCAL;
@@ -694,18 +741,11 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
     }
     sync_n<BAR>(nthr);
     {
-        const double omega = sh.sc[0], N = sh.sc[2], aphi = sh.sc[5], bom = sh.sc[6];
+        const double omega = sh.sc[0], bom = sh.sc[6];
         for (int idx = tid; idx < R * R; idx += nthr) {
             const int i = idx / R, j = idx % R;
-            const double pn = simp ? sh.Pb[idx] : bom * sh.aug[FIN][sh.perm[i]][R + j];      // rPSMF.py:106
-            const double vn = aphi * (sh.V[idx] - sh.vx[i] * sh.vxt[j] / N);                 // rPSMF.py:115
-            sh.P[idx] = pn;
-            sh.V[idx] = vn;
+            sh.P[idx] = simp ? sh.Pb[idx] : bom * sh.aug[FIN][sh.perm[i]][R + j];          // rPSMF.py:106
             if (!simp) sh.Q[idx] = omega * sh.Q[idx];                                        // rPSMF.py:133
-        }
-        if (tid >= nthr - R) {
-            const int j = tid - (nthr - R);
-            sh.g[j] = (((p.flags & F_CUPDATE_VT) != 0) ? sh.vx[j] : sh.vxt[j]) / N;          // rPSMF.py:111 / PSMF.py:80
         }
         if (tid == nthr - 32) {
             const double lam = sh.lam;

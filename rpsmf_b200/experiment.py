@@ -104,7 +104,9 @@ def run_impute_experiment(Yorig, method="rPSMF", percentage=30, seed=None, repea
     if unknown:
         raise TypeError("unknown hyper-parameters: %s" % sorted(unknown))
     hp.update(hyper)
-    fit = fit or _default_fit(method)
+    if batched and fit is not None:
+        raise ValueError("batched=True uses the CUDA batch kernel; it takes no custom fit")
+    fit = fit or (None if batched else _default_fit(method))
     seed = seed or np.random.randint(10000)                   # rPSMF.py:154
     np.random.seed(seed)
     Yorig = np.asarray(Yorig, dtype=np.float64)
@@ -121,8 +123,6 @@ def run_impute_experiment(Yorig, method="rPSMF", percentage=30, seed=None, repea
     hashes = dict(Y=[], C=[], X=[])
     missRatio = float("nan")
     if batched:
-        if fit is not None:
-            raise ValueError("batched=True uses the CUDA batch kernel; it takes no custom fit")
         from .impute import fit_repeats
         Ys, Cs, Xs, Ms, Mms, Eis = [], [], [], [], [], []
         for i in range(repeats):
