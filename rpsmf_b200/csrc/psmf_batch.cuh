@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(NW * 32, batch_min_ctas(R, NW)) psmf_batch_ker
     __shared__ double red[NW * nstat_pad(R)];
     __shared__ __align__(8) uint64_t cbar;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int series = blockIdx.x;
     const int ntiles = (int)((p.d + TILE - 1) / TILE);
     const int nrows = ntiles * TILE;

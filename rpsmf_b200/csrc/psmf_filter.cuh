@@ -188,6 +188,11 @@ __device__ __forceinline__ void stamp_pass(const KParams& p, int64_t t, int slot
     }
 }
 
+// Warp index as a WARP-UNIFORM value (broadcast from lane 0): the compiler can then see that a branch on it never splits a
+// warp and emits plain SHFL / REDUX in the role-specialised code below it; with `threadIdx.x >> 5` every shuffle is
+// wrapped in WARPSYNC.COLLECTIVE ... ENDCOLLECTIVE (~15 extra cycles each, measured on the one-warp solver).
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ double warp_allsum(double v) {
     __syncwarp();
 #pragma unroll
@@ -680,7 +685,7 @@ __device__ void small_update(const KParams& p, Smem<R>& sh, int tid, int lane, i
         sync_n<BAR>(nthr);
         // the elimination is latency-bound: a subset of the warps runs it (less redundant pivot-search work on
         // the fp64 pipe, cheaper barrier); the first warp past them computes the inverse-free half meanwhile
-        if (tid < NGJ) gauss_jordan_cta<R, NGJ, GJBAR>(sh, tid);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
+        if (warp < NGJ / 32) gauss_jordan_cta<R, NGJ, GJBAR>(sh, tid);   // aug[FIN][perm[k]][R..2R) = K[k][:], [..][2R] = (K b)[k]
         else if (side_warp && warp == NGJ / 32) side_half();
         sync_n<BAR>(nthr);
     }
@@ -953,7 +958,7 @@ __global__ void __launch_bounds__(V1_WARPS * 32, 2) psmf_filter_kernel(const KPa
     double* stage_all = reinterpret_cast<double*>(dyn_smem);                   // NW staging tiles [R][32] fp64
     double* ebuf = stage_all + NW * R * TILE;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int series = blockIdx.x / p.cps;
     const int part = blockIdx.x % p.cps;
     const int ntiles = (int)((p.d + TILE - 1) / TILE);

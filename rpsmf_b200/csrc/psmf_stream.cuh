@@ -455,10 +455,67 @@ template <int R>
 struct ControlSmem {
     Smem<R> sh;
     double tot2[2][nstat2_pad(R)];   // reduced (and exchanged) pipelined sums of step t in tot2[t & 1]
-    double tmp2[nstat2_pad(R)];      // exchange scratch (reducers)
+    double Mw[R][R + 1];             // copy of I + Pbar G for the one-warp solve of K b (the CTA-wide elimination overwrites aug)
     double a2[nstat2_pad(R)];        // A_t packed, h_t, gamma, q0, n_obs (solvers)
     double kb[R];                    // K b
 };
+
+// ---- K b on the critical path: Gauss-Jordan on [M | rhs] by ONE warp, entirely in registers ----------------------
+// The data CTAs wait for x_t = x_bar + K b only; the full K (16 right-hand sides, for P_t) is needed a whole step
+// later.  So one warp solves M z = Pbar b alone while the CTA-wide elimination produces K off the critical path: no
+// shared-memory round trip and no barrier per pivot (shuffles only), ~110 cycles per pivot instead of ~280.
+// Lane (row i = lane & 15, half h = lane >> 4) holds columns [h HC, (h+1) HC) of row i of M, half 0 also the rhs.
+// Partial pivoting as in gauss_jordan_cta (integer max over the high words of |a_ik|, ties -> lowest row); rows are not
+// swapped and pivot rows are not normalised: unknown k = rhs[p_k] / a[p_k][k] at the end.  All 32 lanes must call.
+// Measured (scratch/solve_bench.cu, trace.py): 179 cycles per pivot alone on an SM, but ~2x that next to the CTA-wide
+// elimination it was meant to overtake (shuffles share the MIO pipe with the elimination's shared-memory traffic) -- the
+// data CTAs got x_t 0.5 us LATER than from the 192-thread elimination.  Kept for reference, off by default.
+#ifndef PSMF_WARP_SOLVE
+#define PSMF_WARP_SOLVE 0
+#endif
+constexpr bool WARP_SOLVE = PSMF_WARP_SOLVE != 0;
+
+template <int R>
+__device__ __forceinline__ void warp_solve(const double (*Mw)[R + 1], double rhs, double* __restrict__ z_out, int lane) {
+    static_assert(R <= 16, "one warp holds at most 16 rows");
+    constexpr int HC = (R + 1) / 2;
+    const int i = lane & 15, h = lane >> 4;
+    const bool rowok = i < R;
+    double m[HC];
+#pragma unroll
+    for (int c = 0; c < HC; ++c) {
+        const int gc = h * HC + c;
+        m[c] = (rowok && gc < R) ? Mw[i][gc] : 0.0;
+    }
+    double r = (h == 0 && rowok) ? rhs : 0.0;
+    int mycol = -1;                                    // the unknown this lane's row became the pivot row of
+    double myinv = 0.0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int hk = k / HC, kl = k - hk * HC;                             // compile-time after unrolling
+        const double colk = __shfl_sync(FULL, m[kl], i + 16 * hk);           // a_ik of this lane's row
+        const int hi = __double2hiint(fabs(colk));
+        const int key = (!rowok || mycol >= 0) ? -1 : ((hi & 0x7ffffff0) | (15 - i));
+        const double cinv = fast_rcp(colk);
+        const int pi = 15 - (__reduce_max_sync(FULL, key) & 15);
+        const double inv = __shfl_sync(FULL, cinv, pi);
+        const double f = (i == pi) ? 0.0 : colk * inv;                        // the pivot row itself stays
+#pragma unroll
+        for (int c = 0; c < HC; ++c) {
+            if (HC + c > k) {                                                 // column still live in at least one half
+                const double rp = __shfl_sync(FULL, m[c], pi + 16 * h);
+                m[c] = fma(-f, rp, m[c]);
+            }
+        }
+        const double rr = __shfl_sync(FULL, r, pi + 16 * h);
+        r = fma(-f, rr, r);
+        if (i == pi) {
+            mycol = k;
+            myinv = inv;
+        }
+    }
+    if (h == 0 && rowok && mycol >= 0) z_out[mycol] = r * myinv;
+}
 
 // ---- reducer half of the control CTA -------------------------------------------------------------------
 // One SM ingests only ~40 GB/s, so the ~200 kB of CTA partials of a step (147 CTAs x 173 doubles at r = 16) are
@@ -596,7 +653,7 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
     constexpr int FIN = R & 1;
     Smem<R>& sh = cs.sh;
     double* a2 = cs.a2;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int64_t n = p.n_steps;
     const bool simp = (p.flags & F_SIMPLIFIED) != 0;
     const bool robust = (p.flags & F_ROBUST) != 0;
@@ -665,13 +722,15 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
                         acc1 = fma(sh.Pb[i * R + k + 1], a2[gram_off(R, lo1) + hi1 - lo1], acc1);
                     }
                 }
-                sh.aug[0][i][j] = fma(w1, acc0 + acc1, (i == j) ? 1.0 : 0.0);
+                const double mij = fma(w1, acc0 + acc1, (i == j) ? 1.0 : 0.0);
+                sh.aug[0][i][j] = mij;
+                cs.Mw[i][j] = mij;
                 sh.aug[0][i][R + j] = sh.Pb[i * R + j];
             }
             sync_n<CB_S>(NTHR);
         }
         // (C) elimination (C_GJ threads) next to the side computations (two warps)
-        if (tid < C_GJ) {
+        if (warp < C_GJ / 32) {
             // aug[FIN][perm[k]][R..2R) = K[k][:]   (measured: 128 and 192 threads tie at 2.3 us, 64: 5.8, 32: 9.1)
             if (!simp) gauss_jordan_cta<R, C_GJ, CB_GJ, 2 * R>(sh, tid);
         } else if (warp == C_GJ / 32) {
@@ -706,6 +765,40 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
                 sh.tot[NGm + R + 2] = q0;
                 sh.tot[NGm + R + 3] = a2[NGm + R + 2];
             }
+            if (WARP_SOLVE && !simp) {
+                // K b by this warp alone (warp_solve), then x_t and the publication of xbar_{t+1}: the data CTAs do not
+                // wait for the CTA-wide elimination any more
+                __syncwarp();
+                double rhs = 0.0;
+                if (lane < R) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < R; k += 2) {
+                        s0 = fma(sh.Pb[lane * R + k], sh.tot[NGm + k], s0);
+                        if (k + 1 < R) s1 = fma(sh.Pb[lane * R + k + 1], sh.tot[NGm + k + 1], s1);
+                    }
+                    rhs = s0 + s1;
+                }
+                warp_solve<R>(cs.Mw, rhs, cs.kb, lane);
+                __syncwarp();
+                const double xn = lane < R ? sh.xb[lane] + cs.kb[lane] : 0.0;  // rPSMF.py:104
+                double xnext = xn;                                             // identity; external: set n is never used
+                if (p.dynamics == DYN_LINEAR) {
+                    // x_bar_{t+1} = A x_t + c in the operation order of linear_predict (predict_cta recomputes it from sh.x
+                    // and must get the same bits: the data CTAs see this copy, the control CTA its own)
+                    double acc = (lane < R && p.lin_c != nullptr) ? p.lin_c[lane] : 0.0;
+#pragma unroll
+                    for (int k = 0; k < R; ++k) {
+                        const double xk = __shfl_sync(FULL, xn, k);
+                        if (lane < R) acc = fma(p.lin_A[lane * R + k], xk, acc);
+                    }
+                    xnext = acc;
+                } else if (p.dynamics == DYN_COS && lane < R) {
+                    xnext = cos(__dadd_rn(__dmul_rn(__dmul_rn(6.283185307179586, sh.th[lane]), (double)(p.k0 + t + 1)), xn));
+                }
+                if (lane < R) cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + R + lane, xnext, tag_of((unsigned long long)t + 2ULL));
+                stamp(p, t, 6, C_GJ);
+            }
         } else {
             // eta = (rho n_obs + (rho + a) tr(Pbar G)) / d, N = a + eta, g_t = V x_bar / N   (rPSMF.py:108-111)
             const double a = sh.a, rho = sh.rho;
@@ -731,7 +824,11 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
                 eta = (rho * a2[NGm + R + 2] + (rho + a) * trpg) / dg;
             }
             const double N = a + eta;
-            if (lane < R) sh.g[lane] = (((p.flags & F_CUPDATE_VT) != 0) ? sh.vx[lane] : sh.vxt[lane]) / N;   // rPSMF.py:111 / PSMF.py:80
+            if (lane < R) {
+                const double gl = (((p.flags & F_CUPDATE_VT) != 0) ? sh.vx[lane] : sh.vxt[lane]) / N;   // rPSMF.py:111 / PSMF.py:80
+                sh.g[lane] = gl;
+                if (WARP_SOLVE && !simp) cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + lane, gl, tag_of((unsigned long long)t + 2ULL));
+            }
             if (lane == 0) {
                 sh.sc[1] = eta;
                 sh.sc[2] = N;
@@ -741,21 +838,26 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
         stamp(p, t, 7);
         // (D) x_t = xbar_t + K b, xbar_{t+1} = f(x_t); publish set t+1 = {g_t, xbar_{t+1}}   (warp 0)
         if (warp == 0) {
-            const int j = lane & 15, half = lane >> 4;
+            const bool early = WARP_SOLVE && !simp;       // K b, x_t and the publication were done by the solver warp
             double kbj = 0.0;
-            if (!simp && j < R) {
-                const double* Krow = &sh.aug[FIN][sh.perm[j]][R];
-                double s0 = 0.0, s1 = 0.0;
-                constexpr int H = (R + 1) / 2;
+            if (early) {
+                kbj = lane < R ? cs.kb[lane] : 0.0;
+            } else {
+                const int j = lane & 15, half = lane >> 4;
+                if (!simp && j < R) {
+                    const double* Krow = &sh.aug[FIN][sh.perm[j]][R];
+                    double s0 = 0.0, s1 = 0.0;
+                    constexpr int H = (R + 1) / 2;
 #pragma unroll
-                for (int k = 0; k < H; k += 2) {
-                    const int k0 = half * H + k;
-                    if (k0 < R) s0 = fma(Krow[k0], sh.tot[NGm + k0], s0);
-                    if (k + 1 < H && k0 + 1 < R) s1 = fma(Krow[k0 + 1], sh.tot[NGm + k0 + 1], s1);
+                    for (int k = 0; k < H; k += 2) {
+                        const int k0 = half * H + k;
+                        if (k0 < R) s0 = fma(Krow[k0], sh.tot[NGm + k0], s0);
+                        if (k + 1 < H && k0 + 1 < R) s1 = fma(Krow[k0 + 1], sh.tot[NGm + k0 + 1], s1);
+                    }
+                    kbj = s0 + s1;
                 }
-                kbj = s0 + s1;
+                kbj += __shfl_xor_sync(FULL, kbj, 16);
             }
-            kbj += __shfl_xor_sync(FULL, kbj, 16);
             double xn = 0.0, xnext = 0.0;
             if (lane < R) xn = sh.xb[lane] + kbj;                              // rPSMF.py:104 (simplified: x = x_bar)
             if (p.dynamics == DYN_LINEAR) {
@@ -776,11 +878,12 @@ __device__ void control_solve(const KParams& p, ControlSmem<R>& cs) {
                 } else if (p.dynamics != DYN_LINEAR) {
                     xnext = xn;                        // external dynamics run one step per launch: set n is never used
                 }
-                cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + lane, sh.g[lane], tag_of((unsigned long long)t + 2ULL));
-                cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + R + lane, xnext, tag_of((unsigned long long)t + 2ULL));
-                cs.kb[lane] = kbj;
+                if (!early) {
+                    cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + lane, sh.g[lane], tag_of((unsigned long long)t + 2ULL));
+                    cell_store(cells + (size_t)((t + 1) & 1) * 2 * R + R + lane, xnext, tag_of((unsigned long long)t + 2ULL));
+                }
             }
-            stamp(p, t, 6);
+            if (!early) stamp(p, t, 6);
             // (E) off the critical path: omega, phi, gradient of the step log-likelihood
             const double a = sh.a, rho = sh.rho, lam = sh.lam;
             const double s = sh.tot[NGm + R], q1 = sh.tot[NGm + R + 1], q0 = sh.tot[NGm + R + 2], nobs = sh.tot[NGm + R + 3];
@@ -880,7 +983,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     extern __shared__ __align__(128) unsigned char dyn_smem_s[];
     if (blockIdx.x == gridDim.x - 1) {       // ---- control CTA ----
         ControlSmem<R>& cs = *reinterpret_cast<ControlSmem<R>*>(static_smem);
-        if (threadIdx.x < C_SOLVERS) control_solve<R>(p, cs);
+        if (uniform_warp_id() < C_SOLVERS / 32) control_solve<R>(p, cs);
         else control_reduce<R>(p, cs);
         return;
     }
@@ -888,7 +991,7 @@ __global__ void __launch_bounds__(s_threads(), 1) psmf_stream_kernel(const KPara
     const int NPW = p.npw;                                         // active pass warps (<= V2_PASS_WARPS)
     DataSmem<R>& ps = *reinterpret_cast<DataSmem<R>*>(static_smem);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int part = blockIdx.x;                                   // data CTA index, p.cps data CTAs
     const int ntiles = (int)((p.d + TILE - 1) / TILE);
     const int tb = (int)((int64_t)ntiles * part / p.cps);
