@@ -93,6 +93,15 @@ __device__ __forceinline__ void mbar_wait(const KParams& p, uint64_t* bar, uint3
         if (sp.expired(p, SPIN_MBAR, step)) break;
     }
 }
+// a wait that spans the whole launch (resident producer): no clock, it only gives up when the grid is aborting (the
+// waits of the pass warps it depends on are the bounded ones), and it sleeps between attempts to stay off the pipes
+__device__ __forceinline__ void mbar_wait_launch(const KParams& p, uint64_t* bar, uint32_t parity) {
+    unsigned n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++n & 15u) == 0u && *reinterpret_cast<volatile unsigned long long*>(p.bar + ABORT_WORD) != 0ULL) break;
+        __nanosleep(500);
+    }
+}
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
@@ -183,6 +192,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
     const double* xbp = ps.par[(pass - 1) & 1] + R;
     const double* gl = ps.par[pass & 1];
     const bool has_prev = pass >= 1, has_cur = !FLUSH;
+    const bool first_touch = pass == 0;      // FLUSH of an empty launch (n = 0) is pass 0 as well
     PassAcc acc;
     acc.zero();
     long long wait_full = 0;
@@ -195,7 +205,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
         const int k = tl / TS, i = tl - k * TS;
         const int64_t kk = pass * nchunks + k;
         const int slot = streaming ? (int)(kk % nslot) : k;
-        const uint32_t parity = (uint32_t)((streaming ? kk / nslot : pass) & 1);
+        const uint32_t parity = (uint32_t)(streaming ? (kk / nslot) & 1 : 0);
         unsigned char* sb = slots + (size_t)slot * L::SLOT;
         const long long c0 = clock64();
         // mbarrier waits only know the parity of a phase.  Bulk loads complete out of order, so a warp that jumps
@@ -209,7 +219,9 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
                 if (sp.expired(p, SPIN_RING, pass)) break;
             }
         }
-        mbar_wait(p, &ps.full[slot], parity, pass);
+        // resident: tile tl belongs to this warp in every pass and nobody else touches it between the initial load and the
+        // final store, so only the first pass waits for the load (phase 0 of full[k]) and only the flush pass releases it
+        if (streaming || first_touch) mbar_wait(p, &ps.full[slot], parity, pass);
         wait_full += clock64() - c0;
         const int64_t row = (int64_t)(tb + tl) * TILE + lane;
         const int rl = tl * TILE + lane;
@@ -220,7 +232,7 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
         if ((p.flags & F_DBG_NOCOMPUTE) != 0) {
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && (streaming || FLUSH)) {
                 const int ntc = min(TS, nt - k * TS);
                 mbar_arrive_n(&ps.done[slot], (i == ntc - 1) ? (uint32_t)(TS - ntc + 1) : 1u);
             }
@@ -298,11 +310,13 @@ __device__ __forceinline__ void s_warp_pass(const KParams& p, DataSmem<R>& ps, d
         }
         // this warp is done with its tile: make the generic-proxy writes visible to the bulk store and
         // release the slot (the owner of the last tile of a partial chunk also signs for the missing tiles)
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            const int ntc = min(TS, nt - k * TS);
-            mbar_arrive_n(&ps.done[slot], (i == ntc - 1) ? (uint32_t)(TS - ntc + 1) : 1u);
+        if (streaming || FLUSH) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const int ntc = min(TS, nt - k * TS);
+                mbar_arrive_n(&ps.done[slot], (i == ntc - 1) ? (uint32_t)(TS - ntc + 1) : 1u);
+            }
         }
     }
     if constexpr (!FLUSH) {
@@ -420,13 +434,9 @@ __device__ void s_producer(const KParams& p, DataSmem<R>& ps, unsigned char* slo
             mbar_arrive_expect_tx(&ps.full[k], bytes);
             bulk_load(slots + (size_t)k * L::SLOT, Cb + (size_t)k * CHUNK_ELEMS, bytes, &ps.full[k]);
         }
-        for (int64_t pass = 1; pass < npass; ++pass)
-            for (int k = 0; k < nchunks; ++k) {
-                mbar_wait(p, &ps.done[k], (uint32_t)((pass - 1) & 1), pass);               // pass warps are done with pass-1
-                mbar_arrive(&ps.full[k]);                                          // C stays resident
-            }
+        // C stays resident: the pass warps only sign off after the flush pass (phase 0 of done[k])
         for (int k = 0; k < nchunks; ++k) {
-            mbar_wait(p, &ps.done[k], (uint32_t)((npass - 1) & 1), npass);
+            mbar_wait_launch(p, &ps.done[k], 0u);
             bulk_store(Cb + (size_t)k * CHUNK_ELEMS, slots + (size_t)k * L::SLOT, k == nchunks - 1 ? last_bytes : full_bytes);
             bulk_commit();
         }
