@@ -57,9 +57,10 @@ def parse():
     ap.add_argument("--window", type=int, default=500, help="filter steps per kernel launch (= per bench step)")
     ap.add_argument("--mask", default="iid", choices=["iid", "segments"],
                     help="missing pattern: iid Bernoulli (default) or runs of 20 steps per row (common.py:50-76)")
-    ap.add_argument("--mask-encoding", default="bytes", choices=["bytes", "nan"],
-                    help="bytes: zero-filled y + one mask byte per entry (rPSMF.py:198-202); nan: missing entries are NaN in y "
-                         "(the raw data form, rPSMF.py:160-164), no mask stream")
+    ap.add_argument("--mask-encoding", default="nan", choices=["bytes", "nan"],
+                    help="nan (default): missing entries are NaN in y -- the raw data form the reference ingests "
+                         "(rPSMF.py:160-164) -- and there is no mask stream (SURVEY.md 8(d): 0 mask bytes); bytes: zero-filled y "
+                         "+ one mask byte per entry (rPSMF.py:198-202)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0)
@@ -131,26 +132,28 @@ def regime_of(c_bytes):
 def config_record(args, world):
     d, r, T, W = args.d, args.r, max(args.T // args.window, 1) * args.window, args.window
     esize = 8 if args.dtype == "f64" else 4
+    mb = 0 if args.mask_encoding == "nan" else 1                # mask bytes per entry
+    ym = "NaN-encoded Y" if mb == 0 else "Y/M"
     if args.workload == "B":
         S = args.series
         return dict(workload="B: %d independent rPSMF series of d=%d r=%d T=%d, 20%% missing, %s; one bench step = one kernel launch "
                              "over %d filter steps of every series" % (S, d, r, T, args.dtype, W),
                     series=S, d=d, r=r, T=T, window=W, missing=0.2, mask=args.mask, mask_encoding=args.mask_encoding, robust=True,
                     series_per_gpu=S // world,
-                    l2_policy="C of every series (%.0f kB) is resident in shared memory for the whole launch; Y/M windows "
+                    l2_policy="C of every series (%.0f kB) is resident in shared memory for the whole launch; %s windows "
                               "(%.1f GB per GPU) are larger than L2 and stream from HBM" %
-                              (d * r * esize / 1e3, (S // world) * W * d * (esize + 1) / 1e9),
+                              (d * r * esize / 1e3, ym, (S // world) * W * d * (esize + mb) / 1e9),
                     parallelism="series split over %d GPU(s), no communication" % world)
     from rpsmf_b200 import shard_rows
     d_loc = max(b - a for a, b in (shard_rows(d, world, k) for k in range(world)))
     regime = regime_of(d_loc * r * esize)
-    pol = {"hbm": "inputs larger than L2: C (%.0f MB) and the Y/M windows (%.1f GB) stream from HBM every filter step",
+    pol = {"hbm": "inputs larger than L2: C (%.0f MB) and the YM windows (%.1f GB) stream from HBM every filter step",
            "hbm+l2": "C shard (%.0f MB) streams through the chunk ring and partly stays in the 126 MB L2 between filter steps (by "
-                     "design: it is re-read every step); Y/M windows (%.1f GB) are larger than L2 and stream from HBM",
+                     "design: it is re-read every step); YM windows (%.1f GB) are larger than L2 and stream from HBM",
            "l2": "C shard (%.0f MB) streams through the chunk ring but fits the 126 MB L2 (by design: it is re-read every step); "
-                 "Y/M windows (%.1f GB) are larger than L2 and stream from HBM",
-           "smem": "C shard (%.0f MB) is resident in shared memory for the whole launch; Y/M windows (%.1f GB) are larger than "
-                   "L2 and stream from HBM"}[regime] % (d_loc * r * esize / 1e6, W * d_loc * (esize + 1) / 1e9)
+                 "YM windows (%.1f GB) are larger than L2 and stream from HBM",
+           "smem": "C shard (%.0f MB) is resident in shared memory for the whole launch; YM windows (%.1f GB) are larger than "
+                   "L2 and stream from HBM"}[regime].replace("YM", ym) % (d_loc * r * esize / 1e6, W * d_loc * (esize + mb) / 1e9)
     return dict(workload="L: rPSMF d=%d r=%d T=%d, 20%% missing, %s; one bench step = one kernel launch over %d filter steps"
                          % (d, r, T, args.dtype, W),
                 d=d, r=r, T=T, window=W, missing=0.2, mask=args.mask, mask_encoding=args.mask_encoding, robust=True,
@@ -700,10 +703,11 @@ def run_nccl_baseline(ctx):
     row0, row1 = shard_rows(d, world, rank)
     d_loc = row1 - row0
     T = W * 4
-    Y, M, C0, x0 = bd.make_series(torch, dev, d_loc, row0, d, r, T, dtype, mask=args.mask)
+    nan_enc = args.mask_encoding == "nan"
+    Y, M, C0, x0 = bd.make_series(torch, dev, d_loc, row0, d, r, T, dtype, mask=args.mask, nan_encoded=nan_enc)
     init = init_state(r)
     eng = FilterEngine(d_loc, r, dtype=dtype, robust=True, device=ctx["local_rank"], d_global=d, world_size=world, rank=rank,
-                       exchange="external")
+                       exchange="external", nan_mask=nan_enc)
     eng.set_state(C_=C0.to(dtype), V=init["V"], P=init["P"], x=x0, Q=init["Q"], rho=[init["rho"]], lam=[init["lam"]])
     stats = eng.stats_buffer()
 
@@ -715,7 +719,7 @@ def run_nccl_baseline(ctx):
     X = torch.empty((T, r), dtype=torch.float64, device=dev)
 
     def one_filter_step(t, k):
-        eng.run_split(Y[t:t + 1], M[t:t + 1], k0=k, allreduce=allreduce, X_out=X[t:t + 1])
+        eng.run_split(Y[t:t + 1], None if M is None else M[t:t + 1], k0=k, allreduce=allreduce, X_out=X[t:t + 1])
 
     for t in range(min(W, 20)):
         one_filter_step(t, 1 + t)
