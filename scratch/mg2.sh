@@ -4,11 +4,12 @@ N=$1; TAG=$2
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 $TR --master-port 29511 tests/multi_gpu_check.py > gpurun_out/${TAG}_multi_gpu_check_n$N.log 2>&1; echo "multi_gpu_check rc=$? OK lines: $(grep -c ' OK' gpurun_out/${TAG}_multi_gpu_check_n$N.log)"
 $TR --master-port 29512 bench.py --gpus $N > gpurun_out/${TAG}_bench_L_n$N.json 2> gpurun_out/${TAG}_bench_L_n$N.err; echo "bench L rc=$?"
-for v in $VARIANTS; do
-  PSMF_B200_LIB=$PWD/rpsmf_b200/variants/lib_$v.so $TR --master-port 29513 bench.py --gpus $N --steps 10 --no-e2e --no-cpu > gpurun_out/${TAG}_bench_L_n${N}_$v.json 2>/dev/null; echo "variant $v rc=$?"
+for v in $VARIANTS; do  # optional kernel variants (scratch/libs)
+  PSMF_B200_LIB=$PWD/scratch/libs/lib$v.so $TR --master-port 29513 bench.py --gpus $N --steps 10 --no-e2e --no-cpu > gpurun_out/${TAG}_bench_L_n${N}_$v.json 2>/dev/null; echo "variant $v rc=$?"
 done
 $TR --master-port 29514 bench.py --gpus $N --workload B --steps 6 --T 1500 > gpurun_out/${TAG}_bench_B_n$N.json 2> gpurun_out/${TAG}_bench_B_n$N.err; echo "bench B rc=$?"
 $TR --master-port 29515 bench.py --gpus $N --impl nccl --steps 3 --window 100 > gpurun_out/${TAG}_bench_nccl_n$N.json 2> gpurun_out/${TAG}_bench_nccl_n$N.err; echo "bench nccl rc=$?"
+nvidia-smi topo -m > gpurun_out/${TAG}_topo_n$N.log 2>&1
 python - <<PY
 import json,glob
 for f in sorted(glob.glob("gpurun_out/${TAG}_bench_*_n$N*.json")):
