@@ -308,6 +308,26 @@ def measure_l2_copy_gbs(torch, dev, mbytes=16):
     return best
 
 
+def measure_hbm_copy_gbs(torch, dev, seconds=1.0, mbytes=1024):
+    """Plain device copy (read + write bytes) of a buffer pair far larger than L2, back to back for ~`seconds`: the copy
+    bandwidth THIS GPU sustains right after the timed region, under the same power / clock conditions.  Reported next to
+    the roofline (informative); `roofline.peak` stays the driver-measured burst figure of MEASURED_PEAKS.json."""
+    n = mbytes * 1024 * 1024 // 8
+    a = torch.zeros(n, dtype=torch.float64, device=dev)
+    b = torch.empty_like(a)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        b.copy_(a)
+    torch.cuda.synchronize(dev)
+    reps = max(10, int(seconds * 6.0e12 / (2 * n * 8)))
+    e0.record()
+    for _ in range(reps):
+        b.copy_(a)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return reps * 2 * n * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def traffic_for(d_loc, r, dtype, W):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of the same
     shard size (profiles/traffic_r02.json; the N-GPU shard profiled on one GPU -- the kernel's traffic depends on its rows
@@ -476,6 +496,13 @@ def run_workload_L(ctx):
             roofline["note"] = "the C shard (%.0f MB) partly stays in the 126 MB L2 between steps: frac can exceed 1 against the HBM peak" % (
                 d_loc * r * esize / 1e6)
     achieved = alg * W / mean_launch_s / 1e9
+    if regime == "hbm" and world == 1:
+        try:
+            roofline["copy_sustained_gbs_now"] = measure_hbm_copy_gbs(torch, dev)
+            roofline["copy_sustained_note"] = ("torch copy of a 1 GiB buffer pair for ~1 s on this GPU right after the timed region "
+                                               "(informative: what a plain copy sustains under the same power cap)")
+        except Exception:
+            pass
     roofline.update(achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic_for(d_loc, r, args.dtype, W),
                     algorithmic_bytes_per_filter_step=alg, kernel=kname, mean_launch_ms=float(np.mean(per_launch_ms)), regime=regime)
 
