@@ -164,14 +164,17 @@ class PSMFIter:
         self._P = {0: latest(self._P, self.P0)}
         self._V = {0: latest(self._V, self.V0)}
         self._gradsum = np.zeros(np.asarray(self.theta0).shape)
+        self._yrec_from = None
 
     def step(self, y, i, T):
         self.step_reset()
         self._sweep(y, None, self._theta[i - 1], 1, T)
 
-    def _sweep(self, y, m, theta, k_first, k_last):
+    def _sweep(self, y, m, theta, k_first, k_last, materialize=True):
         """Filter steps k_first..k_last (1-based, inclusive) with a fixed theta; state dicts move from
-        key k_first - 1 to key k_last."""
+        key k_first - 1 to key k_last.  ``materialize=False`` (inner blocks of the Recursive variants): the state and the
+        predictions stay on the device -- only the status word and the r-dim theta-gradient cross PCIe -- and the host
+        dicts are filled by the next materialising sweep, for all the steps filtered since the last one."""
         eng = self._get_engine()
         T_all = max(y.keys()) if isinstance(y, dict) else len(y)
         Yd, Md = self._device_y(y, T_all, m)
@@ -186,34 +189,43 @@ class PSMFIter:
         n = k_last - k_first + 1
         ysl = Yd[k_first - 1:k_last]
         msl = None if Md is None else Md[k_first - 1:k_last]
+        # one-step predictions of the steps filtered since the last materialising sweep: (T, d) on the device
+        buf = getattr(self, "_yrec_dev", None)
+        if buf is None or buf.shape != Yd.shape or buf.device != Yd.device:
+            buf = self._yrec_dev = torch.empty_like(Yd)
+            self._yrec_from = k_first
+        if getattr(self, "_yrec_from", None) is None:
+            self._yrec_from = k_first
         if self._dyn == _capi.DYN_EXTERNAL:
-            Yrec = self._sweep_external(eng, ysl, msl, theta, k_first, n)     # accumulates self._gradsum itself
+            buf[k_first - 1:k_last] = self._sweep_external(eng, ysl, msl, theta, k_first, n)     # accumulates self._gradsum itself
             grad = None
         else:
-            out = eng.run(ysl, msl, k0=k_first, want_X=False, want_Yrec=True,
+            out = eng.run(ysl, msl, k0=k_first, want_X=False, Yrec_out=buf[k_first - 1:k_last].unsqueeze(0),
                           want_grad=self._dyn == _capi.DYN_COS)
-            Yrec = out["Yrec"]
             grad = out.get("grad")
         bad = eng.status()
         if bad >= 0:
             raise FloatingPointError("non-finite filter state at step %d" % (k_first + bad))
-        st = eng.get_state()
-        Yh = Yrec.to(torch.float64).cpu().numpy()
-        if Md is not None:
-            Yh = Yh * msl.cpu().numpy()                       # masked prediction, rpsmf.py:229-230
-        for j in range(n):
-            self._y_pred[k_first + j] = Yh[j].reshape(self._d, 1)
-        self._C = {k_last: st["C"].to(torch.float64).cpu().numpy()}
-        self._mu = {k_last: st["x"].cpu().numpy().reshape(self._r, 1)}
-        self._P = {k_last: st["P"].cpu().numpy()}
-        self._V = {k_last: st["V"].cpu().numpy()}
         if grad is not None:
             g = grad.cpu().numpy().reshape(-1)
             gs = np.zeros(self._gradsum.size)
             gs[: min(gs.size, g.size)] = g[: gs.size]
             self._gradsum = self._gradsum + gs.reshape(self._gradsum.shape)
-        self._after_sweep(st, k_last)
         self._state_on_device = True
+        if not materialize:
+            return
+        k_from, self._yrec_from = self._yrec_from, None
+        st = eng.get_state()
+        Yh = buf[k_from - 1:k_last].to(torch.float64).cpu().numpy()
+        if Md is not None:
+            Yh = Yh * Md[k_from - 1:k_last].cpu().numpy()     # masked prediction, rpsmf.py:229-230
+        for j in range(k_last - k_from + 1):
+            self._y_pred[k_from + j] = Yh[j].reshape(self._d, 1)
+        self._C = {k_last: st["C"].to(torch.float64).cpu().numpy()}
+        self._mu = {k_last: st["x"].cpu().numpy().reshape(self._r, 1)}
+        self._P = {k_last: st["P"].cpu().numpy()}
+        self._V = {k_last: st["V"].cpu().numpy()}
+        self._after_sweep(st, k_last)
 
     def _sweep_external(self, eng, ysl, msl, theta, k_first, n):
         """Arbitrary callable dynamics: x_bar and F = df/dx from the host, one step per launch."""
@@ -341,7 +353,8 @@ class _RecursiveMixin:
         ue = max(1, int(self._update_every))
         while k <= T:
             k_last = min(T, ((k - 1) // ue + 1) * ue)
-            self._sweep(y, None, self._theta[k - 1], k, k_last)
+            # state and predictions stay on the device between the blocks; the dicts are filled once, after step T
+            self._sweep(y, None, self._theta[k - 1], k, k_last, materialize=(k_last == T))
             for kk in range(k, k_last):
                 self._carry_theta(kk)
             if k_last % ue == 0:

@@ -4,6 +4,9 @@ d = 20, r = 6, T = 500, cos dynamics, Adam on theta, simplified step), per sweep
     python scratch/synthetic_timing.py reference [sweeps]   # this container (no GPU): ExperimentSynthetic classes, unmodified,
                                                             # autograd replaced by the finite-difference shim of oracle/ref_loader.py
     python scratch/synthetic_timing.py b200 [sweeps]        # GPU box: rpsmf_b200.PSMFIter / rPSMFIter (simplified=True)
+
+Both arms end with the Recursive variants (theta updated inside the sweep, psmf.py:275-331): one pass over the T steps with
+update_every = 1 and 10 (full step, not the simplified one: the experiments have no simplified Recursive class).
 """
 import os, sys, time
 import numpy as np
@@ -71,3 +74,30 @@ for student, seed in ((False, 35853), (True, 35833)):
           % (impl, "rPSMF" if student else "PSMF", d, r, T, best * 1e3, n_iter - 1, T / best, float(np.asarray(o._theta[n_iter]).reshape(-1)[0])), flush=True)
     if hasattr(o, "close"):
         o.close()
+
+
+# ---- Recursive variants: one pass, theta updated every `update_every` steps ----
+if impl == "reference":
+    mod = ref_loader.pypsmf()
+    rec = {False: mod.PSMFRecursive, True: mod.rPSMFRecursive}
+else:
+    from rpsmf_b200 import PSMFRecursive, rPSMFRecursive
+    rec = {False: PSMFRecursive, True: rPSMFRecursive}
+for student, seed in ((False, 35853), (True, 35833)):
+    y, C0, theta0 = gen(seed, student)
+    V0 = 0.1 * np.eye(r); mu0 = 0.3 * np.ones((r, 1)); P0 = 0.5 * np.eye(r); Q = 0.01 * np.eye(r)
+    for ue in (1, 10):
+        best = 1e30
+        for rep in range(3 if impl == "b200" else 1):
+            if student:
+                o = rec[True](theta0, C0, V0, mu0, P0, Q, np.eye(d), 1.8, cosnl)
+            else:
+                o = rec[False](theta0, C0, V0, mu0, P0, {k: Q for k in range(T + 1)}, {k: np.eye(d) for k in range(T + 1)}, cosnl)
+            t0 = time.perf_counter()
+            o.run(y, T, 10, update_every=ue)
+            best = min(best, time.perf_counter() - t0)
+            th = float(np.asarray(o._theta[T]).reshape(-1)[0])
+            if hasattr(o, "close"):
+                o.close()
+        print("%-9s %-15s update_every=%-2d d=%d r=%d T=%d  %8.2f ms per pass  %9.0f filter steps/s  theta[0]=%.9f"
+              % (impl, "rPSMFRecursive" if student else "PSMFRecursive", ue, d, r, T, best * 1e3, T / best, th), flush=True)
