@@ -24,7 +24,7 @@ EVAL_SSE, EVAL_INSIDE, EVAL_COUNT = 0, 1, 2
 MAILBOX_BLOB_BYTES = 128
 SCAL_NAMES = ("a", "eta", "N", "omega", "phi", "sSe", "lam", "rho")
 
-# every symbol include/psmf_b200.h declares (checked by tests/test_capi_symbols.py)
+# every symbol include/psmf_b200.h declares (checked by tests/test_host_cpu.py: the header, this tuple and the built library must agree)
 EXPORTS = (
     "psmf_create", "psmf_destroy", "psmf_last_error", "psmf_version", "psmf_set_state", "psmf_get_state",
     "psmf_run", "psmf_status", "psmf_launch_info", "psmf_launch_info2", "psmf_set_trace", "psmf_mailbox_export", "psmf_mailbox_connect",
