@@ -207,3 +207,32 @@ def test_bench_generator_is_N_invariant_and_segment_mask():
     Yb, Mb, Cb, xb = bd.make_batch(torch, cpu, 0, 6, 6, 32, 3, 20, torch.float64, series_chunk=4)
     Y2, M2, C2, x2 = bd.make_batch(torch, cpu, 2, 3, 6, 32, 3, 20, torch.float64)
     assert torch.equal(Y2, Yb[2:5]) and torch.equal(M2, Mb[2:5]) and torch.equal(C2, Cb[2:5]) and torch.equal(x2, xb[2:5])
+
+
+def test_reference_arm_prints_the_config_record_of_the_cuda_arm():
+    """bench.py --impl reference (the CPU arm the driver times next to the CUDA arm) must describe the same workload: same
+    metric, unit, higher_is_better and an identical `config` record (the driver compares them), plus its own
+    cpu_baseline / e2e objects.  Run here at a tiny size; the record is built from the arguments alone."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    argv = ["--rows", "4096", "--r", "4", "--steps", "1", "--warmup", "0"]
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"] + argv, capture_output=True, text=True,
+                         check=True, cwd=root).stdout
+    line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    old = sys.argv
+    try:
+        sys.argv = ["bench.py"] + argv
+        args = bench.parse()
+    finally:
+        sys.argv = old
+    assert line["impl"] == "reference"
+    assert line["config"] == bench.config_record(args, 1)
+    assert line["config"]["mask_encoding"] == "nan" and line["config"]["d"] == 4096
+    assert line["metric"] == bench.metric_name(args) and line["unit"] == bench.unit_name(args) and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
