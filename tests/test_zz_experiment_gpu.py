@@ -70,3 +70,34 @@ def test_batched_repeats_equal_the_repeat_loop(method):
     for key in ("error_predict", "error_full"):
         assert np.allclose(a["results"][key], b["results"][key], rtol=1e-9, atol=0)
     assert a["results"]["inside_sig"] == b["results"]["inside_sig"]
+
+
+@pytest.mark.parametrize("method", ["rPSMF", "PSMF"])
+def test_published_experiment_replayed_on_the_gpu(method):
+    """One FULL published experiment of the reference -- LondonAir PM2.5, 30 % missing, 100 repeats, seed 123
+    (ExperimentImpute/output/LondonAir_PM25_30_{PSMF,rPSMF}.json, Makefile:160; 192 - 202 s on the authors' machine) --
+    replayed through the drop-in driver with the 100 repeats side by side on the resident batch kernel: the inputs of every
+    repeat hash to the published values and EVERY repeat reproduces the published error_predict / error_full / inside_sig."""
+    import json
+    import time
+    from conftest import load_golden
+    here = os.path.dirname(os.path.abspath(__file__))
+    pub = json.load(open(os.path.join(here, "golden", "published_pm25_30.json")))[method]
+    Yorig = load_golden("impute_pm25_30")["Yorig"]
+    t0 = time.perf_counter()
+    out = ex.run_impute_experiment(Yorig, method, pub["missing_percentage"], seed=pub["seed"], repeats=100, batched=True,
+                                   **{k: v for k, v in pub["parameters"].items() if k != "lambda0" or method == "rPSMF"})
+    wall = time.perf_counter() - t0
+    assert out["hashes"] == pub["hashes"]
+    # (the published `missing_ratio` is not reproduced by the shipped common.prepare_missing even with identical masks --
+    # the file predates the script version in the repository -- so only its range is checked)
+    assert 0.30 <= out["missing_ratio"] < 0.31
+    res, ref = out["results"], pub["results"]
+    for key in ("error_predict", "error_full"):
+        a, b = np.asarray(res[key]), np.asarray(ref[key])
+        assert a.shape == b.shape == (100,)
+        assert np.max(np.abs(a - b) / np.abs(b)) < 1e-8, key
+    # coverage: a ratio of integer counts; an entry within rounding of its 2-sigma bound may fall on the other side
+    assert np.max(np.abs(np.asarray(res["inside_sig"]) - np.asarray(ref["inside_sig"]))) < 1e-4
+    print("\n%s: 100 repeats of the published PM2.5 / 30 %% experiment in %.2f s on the GPU (published runtime of the fits: %.1f s)"
+          % (method, wall, float(np.nansum(ref["runtime"]))))
