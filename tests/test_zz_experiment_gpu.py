@@ -82,7 +82,7 @@ def test_published_experiment_replayed_on_the_gpu(method):
     import time
     from conftest import load_golden
     here = os.path.dirname(os.path.abspath(__file__))
-    pub = json.load(open(os.path.join(here, "golden", "published_pm25_30.json")))[method]
+    pub = json.load(open(os.path.join(here, "golden", "published_results.json")))["files"]["LondonAir_PM25_30_" + method]
     Yorig = load_golden("impute_pm25_30")["Yorig"]
     t0 = time.perf_counter()
     out = ex.run_impute_experiment(Yorig, method, pub["missing_percentage"], seed=pub["seed"], repeats=100, batched=True,
